@@ -1,0 +1,285 @@
+// fasterquant prologue / epilogue data movement: dead columns, damp, act-order permutation,
+// gathers, un-permute + cast.  All HBM-bound byte movers; see include/gptq_b200.h for the
+// reference lines each one replaces.
+#include "common.cuh"
+
+namespace gq {
+
+// ------------------------------------------------------------------ dead columns (gptq.py:143)
+__global__ void dead_columns_kernel(const float* __restrict__ H, int K, int64_t ldh, uint8_t* __restrict__ dead) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K) dead[i] = (H[(int64_t)i * ldh + i] == 0.f) ? 1 : 0;
+}
+
+// One CTA: fix dead diagonal entries, export diag, damp = percdamp * mean(diag) (gptq.py:144,174).
+// Deterministic: fixed-shape tree reduction in fp32 pairs accumulated in double.
+__global__ void __launch_bounds__(1024)
+hessian_prepare_kernel(float* __restrict__ H, int K, int64_t ldh, float percdamp, float* __restrict__ diag_out,
+                       float* __restrict__ damp_out, int32_t* __restrict__ ndead_out) {
+    __shared__ double ssum[32];
+    __shared__ int scnt[32];
+    double acc = 0.0;
+    int cnt = 0;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        float d = H[(int64_t)i * ldh + i];
+        if (d == 0.f) { d = 1.f; H[(int64_t)i * ldh + i] = 1.f; ++cnt; }
+        diag_out[i] = d;
+        acc += (double)d;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = acc; scnt[threadIdx.x >> 5] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0; int c = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { t += ssum[w]; c += scnt[w]; }
+        float mean = (float)(t / (double)K);
+        *damp_out = __fmul_rn(percdamp, mean);
+        if (ndead_out) *ndead_out = c;
+    }
+}
+
+// ------------------------------------------------------------------ W.float() + W[:,dead]=0
+template <typename T>
+__global__ void weights_prepare_kernel(const T* __restrict__ w, int R, int K, int64_t ldw, const uint8_t* __restrict__ dead,
+                                       float* __restrict__ out, int64_t ldo) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    bool dz = dead && dead[c];
+    for (int r = blockIdx.y; r < R; r += gridDim.y) {
+        float v = to_f32<T>(w[(int64_t)r * ldw + c]);
+        out[(int64_t)r * ldo + c] = dz ? 0.f : v;
+    }
+}
+
+// ------------------------------------------------------------------ argsort (gptq.py:166)
+// Rank-by-counting: rank(i) = #{j : v[j] > v[i] or (v[j]==v[i] and j<i)}.  O(n^2) compares,
+// n <= 64K, fully parallel and deterministic (ties broken by ascending index).
+__global__ void __launch_bounds__(256)
+argsort_desc_kernel(const float* __restrict__ v, int n, int32_t* __restrict__ perm, int32_t* __restrict__ invperm) {
+    __shared__ float tile[1024];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float vi = (i < n) ? v[i] : 0.f;
+    int rank = 0;
+    for (int base = 0; base < n; base += 1024) {
+        int m = min(1024, n - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < m; t += blockDim.x) tile[t] = v[base + t];
+        __syncthreads();
+        if (i < n) {
+            for (int t = 0; t < m; ++t) {
+                float vj = tile[t];
+                int j = base + t;
+                rank += (vj > vi) || (vj == vi && j < i);
+            }
+        }
+    }
+    if (i < n) { perm[rank] = i; invperm[i] = rank; }
+}
+
+// ------------------------------------------------------------------ W[:, perm]
+__global__ void permute_cols_kernel(const float* __restrict__ W, int R, int K, int64_t ldw, const int32_t* __restrict__ perm,
+                                    float* __restrict__ out, int64_t ldo) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    int src = perm ? perm[c] : c;
+    for (int r = blockIdx.y; r < R; r += gridDim.y) out[(int64_t)r * ldo + c] = W[(int64_t)r * ldw + src];
+}
+
+// ------------------------------------------------------------------ H[perm][:,perm] + damp, padded
+__global__ void hessian_gather_kernel(const float* __restrict__ H, int K, int64_t ldh, const int32_t* __restrict__ perm,
+                                      const float* __restrict__ damp, float* __restrict__ A, int Kp, int64_t lda) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y;
+    if (j >= Kp) return;
+    float v;
+    if (i < K && j < K) {
+        int pi = perm ? perm[i] : i;
+        int pj = perm ? perm[j] : j;
+        v = H[(int64_t)pi * ldh + pj];
+        if (i == j && damp) v = __fadd_rn(v, *damp);
+    } else {
+        v = (i == j) ? 1.f : 0.f;
+    }
+    A[(int64_t)i * lda + j] = v;
+}
+
+// ------------------------------------------------------------------ mirror lower -> upper
+__global__ void symmetrize_kernel(float* __restrict__ H, int K, int64_t ldh) {
+    // 32x32 tiles through smem: tile (bi,bj) with bj > bi reads the lower tile (bj,bi) transposed.
+    __shared__ float t[32][33];
+    int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        int gi = bj * 32 + r, gj = bi * 32 + tx;     // lower tile element (gi, gj)
+        t[r][tx] = (gi < K && gj < K) ? H[(int64_t)gi * ldh + gj] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        int gi = bi * 32 + r, gj = bj * 32 + tx;     // upper tile element (gi, gj) = lower (gj, gi)
+        if (gi < K && gj < K && gj > gi) H[(int64_t)gi * ldh + gj] = t[tx][r];
+    }
+}
+
+// ------------------------------------------------------------------ staging copy
+template <typename T>
+__global__ void stage_kernel(const T* __restrict__ src, int64_t tokens, int K, int64_t lds, T* __restrict__ dst, int64_t ldd) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ldd) return;
+    for (int64_t t = blockIdx.y; t < tokens; t += gridDim.y)
+        dst[t * ldd + c] = (c < K) ? src[t * lds + c] : from_f32<T>(0.f);
+}
+
+// ------------------------------------------------------------------ Q[:, invperm] + cast
+template <typename T>
+__global__ void finalize_kernel(const float* __restrict__ Q, int64_t ldq, const uint8_t* __restrict__ codes, int64_t ldc, int R,
+                                int K, const int32_t* __restrict__ invperm, T* __restrict__ wout, int64_t ldwo,
+                                uint8_t* __restrict__ cout, int64_t ldco) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    int src = invperm ? invperm[c] : c;
+    for (int r = blockIdx.y; r < R; r += gridDim.y) {
+        if (wout) wout[(int64_t)r * ldwo + c] = from_f32<T>(Q[(int64_t)r * ldq + src]);
+        if (cout) cout[(int64_t)r * ldco + c] = codes[(int64_t)r * ldc + src];
+    }
+}
+
+// ------------------------------------------------------------------ quantize (quant.py:6-10)
+__global__ void quantize_kernel(const float* __restrict__ x, int R, int C, int64_t ldx, const float* __restrict__ scale,
+                                const float* __restrict__ zero, int64_t s_row, int64_t s_col, int maxq,
+                                float* __restrict__ out, int64_t ldo) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    for (int r = blockIdx.y; r < R; r += gridDim.y) {
+        float s = scale[(int64_t)r * s_row + (int64_t)c * s_col];
+        float z = zero[(int64_t)r * s_row + (int64_t)c * s_col];
+        float w = x[(int64_t)r * ldx + c];
+        float q;
+        if (maxq < 0) { float code; q = quant_trits(w, s, z, &code); }
+        else q = dequant(quant_code(w, s, z, (float)maxq), s, z);
+        out[(int64_t)r * ldo + c] = q;
+    }
+}
+
+static inline dim3 grid_cols_rows(int cols, int rows, int threads) {
+    int gy = rows < 1 ? 1 : (rows > 4096 ? 4096 : rows);
+    return dim3(cdiv(cols, threads), gy);
+}
+
+}  // namespace gq
+
+using namespace gq;
+
+extern "C" int gptq_b200_dead_columns(const float* H, int K, int64_t ldh, uint8_t* dead, void* stream) {
+    GQ_ARG(H, 1, "null"); GQ_ARG(K >= 0, 2, "K<0"); GQ_ARG(ldh >= K, 3, "ldh<K"); GQ_ARG(dead, 4, "null");
+    if (K == 0) return 0;
+    dead_columns_kernel<<<cdiv(K, 256), 256, 0, as_stream(stream)>>>(H, K, ldh, dead);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_hessian_prepare(float* H, int K, int64_t ldh, float percdamp, float* diag_out,
+                                         float* damp_out, int32_t* ndead_out, void* stream) {
+    GQ_ARG(H, 1, "null"); GQ_ARG(K > 0, 2, "K<=0"); GQ_ARG(ldh >= K, 3, "ldh<K");
+    GQ_ARG(diag_out, 5, "null"); GQ_ARG(damp_out, 6, "null");
+    hessian_prepare_kernel<<<1, 1024, 0, as_stream(stream)>>>(H, K, ldh, percdamp, diag_out, damp_out, ndead_out);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_weights_prepare(const void* weight, int dtype, int R, int K, int64_t ldw, const uint8_t* dead,
+                                         float* W32, int64_t ldw32, void* stream) {
+    GQ_ARG(weight, 1, "null"); GQ_ARG(dtype >= 0 && dtype <= 2, 2, "dtype"); GQ_ARG(R >= 0, 3, "R<0");
+    GQ_ARG(K >= 0, 4, "K<0"); GQ_ARG(ldw >= K, 5, "ldw<K"); GQ_ARG(W32, 7, "null"); GQ_ARG(ldw32 >= K, 8, "ldw32<K");
+    if (R == 0 || K == 0) return 0;
+    dim3 g = grid_cols_rows(K, R, 256);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == GPTQ_B200_F16) weights_prepare_kernel<__half><<<g, 256, 0, st>>>((const __half*)weight, R, K, ldw, dead, W32, ldw32);
+    else if (dtype == GPTQ_B200_BF16) weights_prepare_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)weight, R, K, ldw, dead, W32, ldw32);
+    else weights_prepare_kernel<float><<<g, 256, 0, st>>>((const float*)weight, R, K, ldw, dead, W32, ldw32);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_argsort_desc(const float* v, int n, int32_t* perm, int32_t* invperm, void* stream) {
+    GQ_ARG(v, 1, "null"); GQ_ARG(n >= 0, 2, "n<0"); GQ_ARG(perm, 3, "null"); GQ_ARG(invperm, 4, "null");
+    if (n == 0) return 0;
+    argsort_desc_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(v, n, perm, invperm);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_permute_cols(const float* W, int R, int K, int64_t ldw, const int32_t* perm, float* out,
+                                      int64_t ldo, void* stream) {
+    GQ_ARG(W, 1, "null"); GQ_ARG(R >= 0, 2, "R<0"); GQ_ARG(K >= 0, 3, "K<0"); GQ_ARG(ldw >= K, 4, "ldw<K");
+    GQ_ARG(out, 6, "null"); GQ_ARG(ldo >= K, 7, "ldo<K");
+    if (R == 0 || K == 0) return 0;
+    permute_cols_kernel<<<grid_cols_rows(K, R, 256), 256, 0, as_stream(stream)>>>(W, R, K, ldw, perm, out, ldo);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_hessian_gather(const float* H, int K, int64_t ldh, const int32_t* perm, const float* damp,
+                                        float* A, int Kp, int64_t lda, void* stream) {
+    GQ_ARG(H, 1, "null"); GQ_ARG(K > 0, 2, "K<=0"); GQ_ARG(ldh >= K, 3, "ldh<K"); GQ_ARG(A, 6, "null");
+    GQ_ARG(Kp >= K && Kp % 128 == 0, 7, "Kp must be >= K and a multiple of 128"); GQ_ARG(lda >= Kp, 8, "lda<Kp");
+    hessian_gather_kernel<<<dim3(cdiv(Kp, 256), Kp), 256, 0, as_stream(stream)>>>(H, K, ldh, perm, damp, A, Kp, lda);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_symmetrize(float* H, int K, int64_t ldh, void* stream) {
+    GQ_ARG(H, 1, "null"); GQ_ARG(K >= 0, 2, "K<0"); GQ_ARG(ldh >= K, 3, "ldh<K");
+    if (K == 0) return 0;
+    int nb = cdiv(K, 32);
+    symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, as_stream(stream)>>>(H, K, ldh);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_stage_input(const void* src, int dtype, int64_t tokens, int K, int64_t ld_src, void* dst,
+                                     int64_t ld_dst, void* stream) {
+    GQ_ARG(src, 1, "null"); GQ_ARG(dtype == GPTQ_B200_F16 || dtype == GPTQ_B200_BF16, 2, "dtype must be f16/bf16");
+    GQ_ARG(tokens >= 0, 3, "tokens<0"); GQ_ARG(K > 0, 4, "K<=0"); GQ_ARG(ld_src >= K, 5, "ld_src<K");
+    GQ_ARG(dst, 6, "null"); GQ_ARG(ld_dst >= K && ld_dst % 8 == 0, 7, "ld_dst must be >= K and a multiple of 8");
+    if (tokens == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (ld_src == K && ld_dst == K) {   // dense -> dense: one bulk device copy
+        GQ_CUDA(cudaMemcpyAsync(dst, src, (size_t)tokens * K * 2, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    dim3 g(cdiv(ld_dst, 256), (unsigned)(tokens > 4096 ? 4096 : tokens));
+    if (dtype == GPTQ_B200_F16) stage_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, tokens, K, ld_src, (__half*)dst, ld_dst);
+    else stage_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, tokens, K, ld_src, (__nv_bfloat16*)dst, ld_dst);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_finalize(const float* Q, int64_t ldq, const uint8_t* codes, int64_t ldc, int R, int K,
+                                  const int32_t* invperm, void* weight_out, int dtype, int64_t ldwo, uint8_t* codes_out,
+                                  int64_t ldco, void* stream) {
+    GQ_ARG(Q, 1, "null"); GQ_ARG(ldq >= K, 2, "ldq<K"); GQ_ARG(R >= 0, 5, "R<0"); GQ_ARG(K >= 0, 6, "K<0");
+    GQ_ARG(dtype >= 0 && dtype <= 2, 9, "dtype");
+    GQ_ARG(!codes_out || codes, 3, "codes_out needs codes");
+    if (R == 0 || K == 0) return 0;
+    dim3 g = grid_cols_rows(K, R, 256);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == GPTQ_B200_F16) finalize_kernel<__half><<<g, 256, 0, st>>>(Q, ldq, codes, ldc, R, K, invperm, (__half*)weight_out, ldwo, codes_out, ldco);
+    else if (dtype == GPTQ_B200_BF16) finalize_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(Q, ldq, codes, ldc, R, K, invperm, (__nv_bfloat16*)weight_out, ldwo, codes_out, ldco);
+    else finalize_kernel<float><<<g, 256, 0, st>>>(Q, ldq, codes, ldc, R, K, invperm, (float*)weight_out, ldwo, codes_out, ldco);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_quantize(const float* x, int R, int C, int64_t ldx, const float* scale, const float* zero,
+                                  int64_t s_row, int64_t s_col, int maxq, float* out, int64_t ldo, void* stream) {
+    GQ_ARG(x, 1, "null"); GQ_ARG(R >= 0, 2, "R<0"); GQ_ARG(C >= 0, 3, "C<0"); GQ_ARG(ldx >= C, 4, "ldx<C");
+    GQ_ARG(scale && zero, 5, "null"); GQ_ARG(out, 10, "null"); GQ_ARG(ldo >= C, 11, "ldo<C");
+    if (R == 0 || C == 0) return 0;
+    quantize_kernel<<<grid_cols_rows(C, R, 256), 256, 0, as_stream(stream)>>>(x, R, C, ldx, scale, zero, s_row, s_col, maxq, out, ldo);
+    GQ_LAUNCHED();
+    return 0;
+}

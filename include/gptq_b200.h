@@ -1,0 +1,179 @@
+/*
+ * gptq_b200 -- C ABI of the B200-native GPTQ layer-wise quantization hot path.
+ *
+ * One shared library (libgptq_b200.so), plain pointers and sizes, no torch types.
+ * The reference (JerryZhou54/gptq) has NO native boundary on this path: every step below is a
+ * chain of eager torch ops inside gptq.py / quant.py.  Each entry point therefore cites the
+ * reference Python lines whose arithmetic it replaces; INTEGRATION.md shows the ctypes binding
+ * a reference maintainer would add to gptq.py / quant.py.
+ *
+ * Conventions (all functions):
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - matrices are row-major with an explicit leading dimension in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream);
+ *   - nothing allocates: ops that need scratch take (ws, ws_bytes) sized by *_workspace_bytes();
+ *   - nothing synchronises the host; work is enqueued on `stream`;
+ *   - return 0 on success, -k if argument k (1-based) is invalid, >0 for a CUDA error code;
+ *     gptq_b200_last_error() returns a thread-local message for the last non-zero return.
+ *   - no global mutable state besides a per-process cache of kernel attributes.
+ */
+#ifndef GPTQ_B200_H
+#define GPTQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPTQ_B200_ABI_VERSION 1
+
+enum { GPTQ_B200_F16 = 0, GPTQ_B200_BF16 = 1, GPTQ_B200_F32 = 2 };
+
+int         gptq_b200_abi_version(void);
+const char* gptq_b200_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py "gpu_launches"). */
+int64_t     gptq_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) Hessian accumulation.  Replaces gptq.py:59-65 (H *= n/(n+1); H += X X^T with
+ *     X = sqrt(2/n) inp^T): the caller folds the running-mean factors into alpha/beta.
+ *
+ *     H[0:K,0:K] <- beta * H + alpha * X^T X      (X: [tokens, K], f16 or bf16, ldx % 8 == 0)
+ *
+ *     tcgen05.mma kind::f16 (fp32 accumulate in TMEM) fed by TMA.  Only the 128x256 tiles that
+ *     intersect the LOWER triangle are computed; entries of H above those tiles are left
+ *     untouched -- call gptq_b200_symmetrize() before reading H as a full matrix.
+ *     `chunk_tokens` (0 = default) bounds how many tokens are summed inside the tensor-core
+ *     accumulator before being added to H in fp32 (round-to-nearest) by the epilogue.
+ * ------------------------------------------------------------------------------------------ */
+size_t gptq_b200_syrk_workspace_bytes(int K, int64_t tokens);
+int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, int K, int64_t ldx,
+                         float* H, int64_t ldh, float alpha, float beta, int chunk_tokens,
+                         void* ws, size_t ws_bytes, void* stream);
+/* Plain CUDA-core fp32 X^T X with the same contract (test cross-check for the tensor path;
+ * never called by the Python package). */
+int gptq_b200_syrk_accum_simt(const void* X, int dtype, int64_t tokens, int K, int64_t ldx,
+                              float* H, int64_t ldh, float alpha, float beta, void* stream);
+/* H[i,j] <- H[j,i] for j > i (mirror the lower triangle). */
+int gptq_b200_symmetrize(float* H, int K, int64_t ldh, void* stream);
+/* Copy one calibration batch [tokens,K] (any ld) into a staging slab with ld_dst % 8 == 0. */
+int gptq_b200_stage_input(const void* src, int dtype, int64_t tokens, int K, int64_t ld_src,
+                          void* dst, int64_t ld_dst, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) fasterquant prologue.  Replaces gptq.py:130-145 (clone().float(), dead columns),
+ *     gptq.py:165-169 (act-order argsort + gathers) and gptq.py:174-176 (damp).
+ * ------------------------------------------------------------------------------------------ */
+/* dead = diag(H)==0: H[dead,dead]=1; diag_out[K] = diag(H); *damp_out = percdamp*mean(diag). */
+int gptq_b200_hessian_prepare(float* H, int K, int64_t ldh, float percdamp,
+                              float* diag_out, float* damp_out, int32_t* ndead_out, void* stream);
+/* W32[r,c] = (float)weight[r,c], 0 where diag[c] was dead (diag_fixed[c]==1 && flagged). */
+int gptq_b200_weights_prepare(const void* weight, int dtype, int R, int K, int64_t ldw,
+                              const uint8_t* dead /*[K] or NULL*/, float* W32, int64_t ldw32,
+                              void* stream);
+/* dead[c] = (H[c,c] == 0) BEFORE hessian_prepare fixes it (call first). */
+int gptq_b200_dead_columns(const float* H, int K, int64_t ldh, uint8_t* dead, void* stream);
+/* perm = argsort(v, descending), ties by ascending index; invperm[perm[i]] = i. */
+int gptq_b200_argsort_desc(const float* v, int n, int32_t* perm, int32_t* invperm, void* stream);
+/* out[r, c] = W[r, perm[c]] */
+int gptq_b200_permute_cols(const float* W, int R, int K, int64_t ldw, const int32_t* perm,
+                           float* out, int64_t ldo, void* stream);
+/* A[i,j] = H[p(i),p(j)] (+ *damp on the diagonal) for i,j < K; identity on the pad [K,Kp).
+ * perm may be NULL (identity).  A is [Kp,Kp], Kp % 128 == 0. */
+int gptq_b200_hessian_gather(const float* H, int K, int64_t ldh, const int32_t* perm,
+                             const float* damp, float* A, int Kp, int64_t lda, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ *     Inverse-Cholesky chain.  Replaces gptq.py:177-179
+ *         H = cholesky(H); H = cholesky_inverse(H); H = cholesky(H, upper=True)
+ *     A (damped, [Kp,Kp], Kp % 128 == 0) is overwritten by U, the upper factor of A^-1
+ *     (A^-1 = U^T U); the strict lower triangle is zeroed.  Computed as U = R^-1 with
+ *     A = R R^T (R upper): one blocked backward Cholesky + one blocked triangular inverse, fp32.
+ *     *info (device int32): 0 ok, i+1 if the pivot at index i was not positive
+ *     (torch.linalg.LinAlgError in the reference).
+ * ------------------------------------------------------------------------------------------ */
+size_t gptq_b200_hinv_upper_workspace_bytes(int Kp);
+int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, int32_t* info,
+                         void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (3) Grid search.  Replaces Quantizer.find_params (quant.py:37-118, weight layout) applied to
+ *     W[:, col0 + g*groupsize : col0 + (g+1)*groupsize] for every group g that starts inside
+ *     [col0, col0+ncols) (the slice is clipped to K like Python slicing).  groupsize <= 0 means
+ *     one group = the whole row range.  Output: scale/zero[r*ldsz + gout0 + g].
+ *     maxq < 0 selects trits (quant.py:69-71).
+ * ------------------------------------------------------------------------------------------ */
+int gptq_b200_find_params(const float* W, int R, int K, int64_t ldw, int col0, int ncols,
+                          int groupsize, int maxq, int sym, int mse, float norm, int grid,
+                          float maxshrink, float* scale, float* zero, int64_t ldsz, int gout0,
+                          void* stream);
+/* quant.py:6-10 elementwise: out = scale*(clamp(round(x/scale)+zero,0,maxq)-zero).
+ * scale/zero index = r*s_row + c*s_col (so [R,1] -> (1,0); per-tensor -> (0,0); [1,C] -> (0,1)). */
+int gptq_b200_quantize(const float* x, int R, int C, int64_t ldx, const float* scale,
+                       const float* zero, int64_t s_row, int64_t s_col, int maxq,
+                       float* out, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ *     Column loop.  Replaces gptq.py:191-276 (standard branch) for all K columns:
+ *     per `blocksize` columns, a persistent-tile kernel keeps each row's W1 slice in registers
+ *     and Hinv1 in shared memory, quantizes column by column with error feedback
+ *     (gptq.py:262-271), then the lazy update W[:, i2:] -= Err1 @ U[i1:i2, i2:] (gptq.py:276)
+ *     runs as an fp32-accurate GEMM.
+ *
+ *     W      [R,K] fp32 working copy (already permuted); destroyed.
+ *     U      upper factor from gptq_b200_hinv_upper.
+ *     gidx   [K] group index of every (permuted) column into scale/zero [R,ngroups].
+ *     mode   0: params given (per-row or static groups) -- scale/zero are inputs;
+ *            1: dynamic groups (gptq.py:253-255): params of group g are fitted to the CURRENT
+ *               W[:, g*gs:(g+1)*gs] when the block containing column g*gs starts (this
+ *               reproduces the reference's stale-weights behaviour for gs < blocksize) and
+ *               written to scale/zero.
+ *     Q      [R,K] fp32 dequantised weights, permuted order.
+ *     codes  [R,K] uint8 integer codes, permuted order (trits: 0/1/2).
+ *     loss   device double: sum(Losses) as printed at gptq.py:294.
+ * ------------------------------------------------------------------------------------------ */
+size_t gptq_b200_colloop_workspace_bytes(int R, int K, int blocksize);
+int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const float* U, int64_t ldu,
+                      int blocksize, int groupsize, int mode, const int32_t* gidx,
+                      float* scale, float* zero, int ngroups, int maxq, int sym, int mse,
+                      float norm, int grid, float maxshrink,
+                      float* Q, int64_t ldq, uint8_t* codes, int64_t ldc, double* loss,
+                      void* ws, size_t ws_bytes, void* stream);
+/* gptq.py:300-305: weight_out[r, c] = (dtype) Q[r, invperm[c]]; codes_out likewise.
+ * invperm may be NULL. */
+int gptq_b200_finalize(const float* Q, int64_t ldq, const uint8_t* codes, int64_t ldc,
+                       int R, int K, const int32_t* invperm, void* weight_out, int dtype,
+                       int64_t ldwo, uint8_t* codes_out, int64_t ldco, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (4) Packing.  Replaces Quant3Linear.pack's loop (quant.py:161-186; bits=3), the 4-bit layout
+ *     of zeroShot/models/quant.py:184-185 (bits=4) and, by analogy, bits=2 and 8.
+ *     qweight is [K*bits/32, R] int32 (K % 32 == 0).
+ *     pack_codes:   from uint8 codes [R,K].
+ *     pack_weights: from dequantised weights, recovering codes as quant.py:153,158 does:
+ *                   round((W + zero*scale)/scale), scale/zero = [R,ngroups] indexed by g_idx[c]
+ *                   (g_idx NULL => group 0).
+ * ------------------------------------------------------------------------------------------ */
+int gptq_b200_pack_codes(const uint8_t* codes, int R, int K, int64_t ldc, int bits,
+                         int32_t* qweight, void* stream);
+int gptq_b200_pack_weights(const void* W, int dtype, int R, int K, int64_t ldw,
+                           const float* scale, const float* zero, int ngroups,
+                           const int32_t* g_idx, int bits, int32_t* qweight, void* stream);
+/* Inverse of pack_codes (for load-time checks and the round-trip tests). */
+int gptq_b200_unpack_codes(const int32_t* qweight, int R, int K, int bits,
+                           uint8_t* codes, int64_t ldc, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ *     fp32 GEMM used by the chain and the lazy update (exposed for tests / roofline runs):
+ *     C[M,N] <- alpha * op(A) op(B) + beta * C,  op = transpose if the flag is set.
+ * ------------------------------------------------------------------------------------------ */
+int gptq_b200_sgemm(int transa, int transb, int M, int N, int Kd, float alpha,
+                    const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                    float* C, int64_t ldc, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPTQ_B200_H */

@@ -1,0 +1,356 @@
+"""GPU parity tests: every C-ABI entry point of libgptq_b200.so against the CPU oracle and the
+reference-generated golden vectors.  Run on the B200 box: ``pytest -m gpu``.
+
+Tolerances (BASELINE.json north_star): packed words bit-exact; H within 1e-5 relative Frobenius;
+codes / dequantised weights agree on >= 99.9 % of entries; sum(Losses) within 1 %.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import gptq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from gptq_b200 import _lib
+    from gptq_b200.gptq import GPTQ
+    from gptq_b200 import quant as Q
+    DEV = torch.device("cuda:0")
+
+
+def _log(**kw):
+    print("  [metric] " + json.dumps(kw))
+
+
+# ------------------------------------------------------------------------------------------ pack
+@pytest.mark.parametrize("bits", [2, 3, 4, 8])
+@pytest.mark.parametrize("R,K", [(40, 96), (64, 128), (200, 352), (1024, 1024)])
+def test_pack_codes_bit_exact(bits, R, K):
+    rng = np.random.default_rng(R * 131 + K + bits)
+    codes = rng.integers(0, 2 ** bits, size=(R, K), dtype=np.uint8)
+    want = O.pack(np.ascontiguousarray(codes.T).astype(np.uint32), bits)
+    got = Q.pack_codes(torch.from_numpy(codes).to(DEV), bits)
+    assert np.array_equal(got.cpu().numpy(), want)
+    back = Q.unpack_codes(got, bits)
+    assert np.array_equal(back.cpu().numpy(), codes)
+
+
+def test_pack_roundtrip_full_size():
+    # Llama-2-7B down_proj shape; size-independent property: unpack(pack(c)) == c, and a checksum of the words
+    R, K = 4096, 11008
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for bits in (2, 3, 4):
+        codes = torch.randint(0, 2 ** bits, (R, K), device=DEV, dtype=torch.uint8, generator=g)
+        qw = Q.pack_codes(codes, bits)
+        assert qw.shape == (K * bits // 32, R)
+        assert torch.equal(Q.unpack_codes(qw, bits), codes)
+        # popcount(words) == sum over codes of popcount(code)
+        pc_words = sum(int(((qw.view(torch.int32) >> s) & 1).sum()) for s in range(32))
+        pc_codes = sum(int(((codes >> s) & 1).sum()) for s in range(bits))
+        assert pc_words == pc_codes
+
+
+def test_pack_weights_matches_reference(golden_A):
+    z, meta = golden_A
+    for name, bits, key in (("b3_perchannel", 3, "qweight3"), ("b4_perchannel", 4, "qweight4")):
+        lin = nn.Linear(meta["K"], meta["R"], bias=False)
+        lin.weight.data = torch.from_numpy(z[f"{name}/Q"])             # CPU fp16, as the reference driver hands it over
+        ql = Q.QuantLinear(bits, meta["K"], meta["R"])
+        ql.pack(lin, torch.from_numpy(z[f"{name}/scale"]), torch.from_numpy(z[f"{name}/zero"]))
+        assert ql.qweight.device.type == "cpu"
+        assert np.array_equal(ql.qweight.numpy(), z[f"{name}/{key}"])
+        if bits == 3:
+            assert np.array_equal(ql.zeros.numpy(), z[f"{name}/pack_zeros"])
+
+
+# ------------------------------------------------------------------------------------------ quantizer
+def test_quantizer_matches_reference(golden_quantizer):
+    z, meta = golden_quantizer
+    for c in meta:
+        q = Q.Quantizer()
+        q.configure(c["bits"], perchannel=c["perchannel"], sym=c["sym"], mse=c.get("mse", False), trits=c.get("trits", False))
+        x = torch.from_numpy(z[c["x"]]).to(DEV)
+        q.find_params(x.clone(), weight=c.get("weight", True))
+        s_ref = torch.from_numpy(z[c["name"] + "/scale"])
+        z_ref = torch.from_numpy(z[c["name"] + "/zero"])
+        assert q.scale.shape == s_ref.shape, c["name"]
+        if c.get("mse", False):
+            # |q-x|^2.4 uses CUDA powf vs torch CPU pow: the argmin may move at near-ties
+            frac = float((q.scale.cpu() == s_ref).float().mean())
+            assert frac >= 0.8, (c["name"], frac)
+            continue
+        assert torch.equal(q.scale.cpu(), s_ref), c["name"]
+        assert torch.equal(q.zero.cpu(), z_ref), c["name"]
+        xq = q.quantize(x)
+        assert torch.equal(xq.cpu(), torch.from_numpy(z[c["name"] + "/xq"])), c["name"]
+
+
+@pytest.mark.parametrize("gs", [-1, 32, 64, 128, 100])
+@pytest.mark.parametrize("sym", [False, True])
+def test_find_params_groups_vs_oracle(gs, sym):
+    g = torch.Generator().manual_seed(3)
+    W = torch.randn(70, 328, generator=g) * 0.03
+    W[5, 64:128] = 0
+    qp = O.QParams(bits=4, sym=sym)
+    s, zr = Q.find_params_groups(W.to(DEV), qp.maxq, sym, groupsize=gs)
+    step = gs if gs > 0 else 328
+    for gi, c0 in enumerate(range(0, 328, step)):
+        so, zo = O.find_params(W[:, c0:c0 + step], qp)
+        assert torch.equal(s[:, gi].cpu(), so.flatten()), (gs, gi)
+        assert torch.equal(zr[:, gi].cpu(), zo.flatten()), (gs, gi)
+
+
+# ------------------------------------------------------------------------------------------ sgemm
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,Kd", [(128, 128, 128), (300, 200, 77), (513, 129, 260), (64, 1000, 128)])
+def test_sgemm(ta, tb, M, N, Kd):
+    g = torch.Generator().manual_seed(M + N + Kd)
+    A = torch.randn((Kd, M) if ta else (M, Kd), generator=g)
+    B = torch.randn((N, Kd) if tb else (Kd, N), generator=g)
+    Cm = torch.randn(M, N, generator=g)
+    want = -0.5 * ((A.t() if ta else A).double() @ (B.t() if tb else B).double()) + 2.0 * Cm.double()
+    Ad, Bd, Cd = A.to(DEV), B.to(DEV), Cm.to(DEV).clone()
+    _lib.check(_lib.load().gptq_b200_sgemm(ta, tb, M, N, Kd, -0.5, Ad.data_ptr(), Ad.stride(0), Bd.data_ptr(), Bd.stride(0),
+                                           2.0, Cd.data_ptr(), N, _lib.stream()), "sgemm")
+    err = O.rel_fro(Cd.cpu(), want)
+    _log(test="sgemm", ta=ta, tb=tb, M=M, N=N, K=Kd, rel=err)
+    assert err < 2e-6
+
+
+# ------------------------------------------------------------------------------------------ Cholesky chain
+def _spd(K, seed, cond_boost=1.0):
+    g = torch.Generator().manual_seed(seed)
+    chan = torch.exp(0.5 * torch.randn(K, generator=g)) * cond_boost
+    X = torch.randn(4 * K, K, generator=g) * chan
+    H = (X.t().double() @ X.double()) * (2.0 / 4)
+    return H.float()
+
+
+def _hinv_upper_gpu(H, percdamp=0.01):
+    lib = _lib.load()
+    K = H.shape[0]
+    Kp = (K + 127) // 128 * 128
+    Hd = H.to(DEV).contiguous()
+    diag = torch.empty(K, device=DEV)
+    damp = torch.empty(1, device=DEV)
+    _lib.check(lib.gptq_b200_hessian_prepare(Hd.data_ptr(), K, K, percdamp, diag.data_ptr(), damp.data_ptr(), 0, _lib.stream()), "prep")
+    A = torch.empty((Kp, Kp), device=DEV)
+    _lib.check(lib.gptq_b200_hessian_gather(Hd.data_ptr(), K, K, 0, damp.data_ptr(), A.data_ptr(), Kp, Kp, _lib.stream()), "gather")
+    info = torch.zeros(1, dtype=torch.int32, device=DEV)
+    n = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
+    ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, info.data_ptr(), ws.data_ptr(), n, _lib.stream()), "hinv")
+    torch.cuda.synchronize()
+    return A[:K, :K].cpu(), int(info.item()), float(damp.item())
+
+
+@pytest.mark.parametrize("K", [128, 200, 256, 640, 1024])
+def test_hinv_upper_vs_fp64(K):
+    H = _spd(K, K)
+    U, info, damp = _hinv_upper_gpu(H)
+    assert info == 0
+    Hd = H.double().clone()
+    Hd += torch.eye(K, dtype=torch.float64) * (0.01 * torch.mean(torch.diag(H)).double())
+    L = torch.linalg.cholesky(Hd)
+    U64 = torch.linalg.cholesky(torch.cholesky_inverse(L), upper=True)
+    U32 = O.hinv_upper(H.clone(), 0.01)                       # the reference's own fp32 3-step route (CPU)
+    e_gpu = O.rel_fro(U, U64)
+    e_ref = O.rel_fro(U32, U64)
+    _log(test="hinv_upper", K=K, rel_gpu_vs_fp64=e_gpu, rel_ref_vs_fp64=e_ref)
+    assert torch.all(torch.tril(U, -1) == 0)
+    assert e_gpu < max(5 * e_ref, 1e-5)
+
+
+def test_hinv_upper_not_pd():
+    H = _spd(256, 5)
+    H[100, 100] = -50.0
+    _, info, _ = _hinv_upper_gpu(H)
+    assert info != 0
+
+
+# ------------------------------------------------------------------------------------------ Hessian syrk
+def _syrk(X, K, kind, alpha=1.0, beta=0.0, H0=None, chunk=0):
+    lib = _lib.load()
+    T = X.shape[0]
+    H = torch.zeros((K, K), device=DEV) if H0 is None else H0.clone()
+    if kind == "tc":
+        n = lib.gptq_b200_syrk_workspace_bytes(K, T)
+        ws = torch.empty(max(n, 16), dtype=torch.uint8, device=DEV)
+        _lib.check(lib.gptq_b200_syrk_accum(X.data_ptr(), _lib.dt(X), T, K, X.stride(0), H.data_ptr(), K, alpha, beta, chunk,
+                                            ws.data_ptr(), n, _lib.stream()), "syrk_accum")
+    else:
+        _lib.check(lib.gptq_b200_syrk_accum_simt(X.data_ptr(), _lib.dt(X), T, K, X.stride(0), H.data_ptr(), K, alpha, beta,
+                                                 _lib.stream()), "syrk_simt")
+    _lib.check(lib.gptq_b200_symmetrize(H.data_ptr(), K, K, _lib.stream()), "symmetrize")
+    torch.cuda.synchronize()
+    return H
+
+
+def _acts(T, K, seed, dtype):
+    g = torch.Generator().manual_seed(seed)
+    chan = torch.exp(0.5 * torch.randn(K, generator=g))
+    return (torch.randn(T, K, generator=g) * chan).to(dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("T,K", [(64, 64), (100, 200), (2048, 256), (2048, 768), (8192, 1024), (4096, 2048), (333, 136)])
+def test_syrk_tc_vs_fp64(T, K, dtype):
+    X = _acts(T, K, T + K, dtype)
+    want = X.double().t() @ X.double()
+    got = _syrk(X.to(DEV), K, "tc")
+    err = O.rel_fro(got.cpu(), want)
+    sim = O.rel_fro(_syrk(X.to(DEV), K, "simt").cpu(), want)
+    _log(test="syrk_tc", T=T, K=K, dtype=str(dtype), rel_tc=err, rel_simt=sim)
+    assert sim < 1e-5
+    assert err < 1e-5
+
+
+def test_syrk_tc_alpha_beta_and_chunks():
+    T, K = 4096, 512
+    X = _acts(T, K, 11, torch.float16)
+    H0 = torch.randn(K, K)
+    H0 = (H0 + H0.t()).to(DEV)
+    want = 0.5 * H0.cpu().double() + 0.25 * (X.double().t() @ X.double())
+    for chunk in (0, 64, 512, 4096):
+        got = _syrk(X.to(DEV), K, "tc", alpha=0.25, beta=0.5, H0=H0, chunk=chunk)
+        err = O.rel_fro(got.cpu(), want)
+        _log(test="syrk_tc_alpha_beta", chunk=chunk, rel=err)
+        assert err < 1e-5
+
+
+def test_syrk_accumulation_bias_long():
+    # long reduction (32768 tokens, all-positive diagonal): exposes tensor-core accumulator rounding
+    T, K = 32768, 256
+    X = _acts(T, K, 5, torch.float16)
+    want = X.double().t() @ X.double()
+    for chunk in (512, 2048, 4096, 32768):
+        got = _syrk(X.to(DEV), K, "tc", chunk=chunk)
+        d = (torch.diag(got.cpu()).double() - torch.diag(want)) / torch.diag(want)
+        _log(test="syrk_bias", chunk=chunk, rel_fro=O.rel_fro(got.cpu(), want), diag_rel_mean=float(d.mean()),
+             diag_rel_max=float(d.abs().max()))
+    assert O.rel_fro(_syrk(X.to(DEV), K, "tc").cpu(), want) < 1e-5
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_add_batch_matches_reference(tag, golden_A, golden_B):
+    z, meta = golden_A if tag == "A" else golden_B
+    lin = nn.Linear(meta["K"], meta["R"], bias=False).half().to(DEV)
+    g = GPTQ(lin)
+    for x in torch.from_numpy(z["X"]):
+        g.add_batch(x.to(DEV), None)
+    assert g.nsamples == meta["nsamples"]
+    H = g.H.cpu()
+    err = O.rel_fro(H, torch.from_numpy(z["H"]))
+    _log(test="add_batch", tag=tag, rel_fro=err)
+    assert err < 1e-5
+    assert torch.equal(H, H.t())
+    im = g.input.cpu()
+    assert torch.allclose(im, torch.from_numpy(z["input_mean"]), rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------ fasterquant
+def _golden_cases(tag):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"gptq_{tag}.npz"))
+    return [(tag, c["name"]) for c in json.loads(bytes(z["meta"]).decode())["cases"]]
+
+
+def _run_gptq(W16, batches, c, H_override=None):
+    R, K = W16.shape
+    lin = nn.Linear(K, R, bias=False).half().to(DEV)
+    lin.weight.data = W16.to(DEV).clone()
+    g = GPTQ(lin)
+    g.quantizer = Q.Quantizer()
+    g.quantizer.configure(c["bits"], perchannel=True, sym=c.get("sym", False), mse=c.get("mse", False), trits=c.get("trits", False))
+    for x in batches:
+        g.add_batch(x.to(DEV), None)
+    if H_override is not None:
+        g.H = H_override.to(DEV).clone()
+    g.fasterquant(blocksize=128, percdamp=c.get("percdamp", .01), groupsize=c.get("groupsize", -1),
+                  actorder=c.get("actorder", False), static_groups=c.get("static_groups", False))
+    return lin, g
+
+
+@pytest.mark.parametrize("tag,name", _golden_cases("A") + _golden_cases("B"))
+def test_fasterquant_matches_reference(tag, name, golden_A, golden_B):
+    z, meta = golden_A if tag == "A" else golden_B
+    c = next(c for c in meta["cases"] if c["name"] == name)
+    W16 = torch.from_numpy(z["W"])
+    lin, g = _run_gptq(W16, list(torch.from_numpy(z["X"])), c)
+    Qref = torch.from_numpy(z[f"{name}/Q"])
+    Qgpu = lin.weight.data.cpu()
+    mism = float((Qgpu != Qref).double().mean())
+    rel_err = abs(g.error - c["error"]) / max(abs(c["error"]), 1e-30)
+    _log(test="fasterquant_golden", tag=tag, case=name, mismatch=mism, err_gpu=g.error, err_ref=c["error"])
+    budget = 1e-3 if not c.get("mse", False) else 5e-2
+    assert mism <= budget
+    assert rel_err <= 1e-2
+    # codes dequantise to the written weights
+    if not c.get("trits", False):
+        s = g.scales[:, g.g_idx.long()]
+        zr = g.zeros[:, g.g_idx.long()]
+        deq = (s * (g.codes.float() - zr)).half()
+        assert torch.equal(deq.cpu(), Qgpu)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(name="opt125m_b4", R=768, K=768, bits=4),
+    dict(name="opt1.3b_b3_g128", R=512, K=2048, bits=3, groupsize=128),
+    dict(name="llama_b4_g128_act_static", R=512, K=1024, bits=4, groupsize=128, actorder=True, static_groups=True),
+    dict(name="bloom_b2_g64", R=384, K=1024, bits=2, groupsize=64),
+    dict(name="opt66b_b3_act", R=256, K=1152, bits=3, actorder=True),
+])
+def test_fasterquant_vs_oracle_medium(cfg):
+    """The five BASELINE.json configurations at reduced width, oracle run live on the host CPU with the SAME H."""
+    R, K = cfg["R"], cfg["K"]
+    g0 = torch.Generator().manual_seed(42)
+    W16 = (torch.randn(R, K, generator=g0) * 0.02).half()
+    batches = [_acts(512, K, 100 + i, torch.float16).unsqueeze(0) for i in range(4)]
+    st = O.HessianState(K)
+    for b in batches:
+        O.add_batch(st, b)
+    qp = O.QParams(bits=cfg["bits"])
+    ref = O.fasterquant(W16, st.H, qp, groupsize=cfg.get("groupsize", -1), actorder=cfg.get("actorder", False),
+                        static_groups=cfg.get("static_groups", False))
+    lin, g = _run_gptq(W16, batches, cfg)
+    Hrel = None
+    mism_codes = 1.0 - O.code_agreement(g.codes.cpu(), ref.codes)
+    mism_q = float((lin.weight.data.cpu() != ref.Q.half()).double().mean())
+    rel_err = abs(g.error - ref.error) / abs(ref.error)
+    rec_gpu = O.recon_error(W16.float(), lin.weight.data.cpu().float(), st.H)
+    rec_ref = O.recon_error(W16.float(), ref.Q, st.H)
+    _log(test="fasterquant_medium", case=cfg["name"], code_mismatch=mism_codes, q_mismatch=mism_q, err_gpu=g.error,
+         err_ref=ref.error, recon_gpu=rec_gpu, recon_ref=rec_ref)
+    assert mism_codes <= 1e-3
+    assert rel_err <= 1e-2
+    assert abs(rec_gpu - rec_ref) <= 1e-2 * rec_ref
+    if cfg.get("actorder", False):
+        assert torch.equal(g.perm.cpu().long(), ref.perm)
+
+
+def test_fasterquant_not_pd_raises():
+    lin = nn.Linear(256, 16, bias=False).half().to(DEV)
+    g = GPTQ(lin)
+    g.quantizer = Q.Quantizer()
+    g.quantizer.configure(4, perchannel=True, sym=False, mse=False)
+    g.add_batch(_acts(64, 256, 1, torch.float16).to(DEV), None)
+    H = g.H
+    H[10, 10] = -1e6
+    g.H = H
+    with pytest.raises(torch.linalg.LinAlgError):
+        g.fasterquant()
+
+
+def test_research_modes_rejected_and_cpu_rejected():
+    lin = nn.Linear(64, 8, bias=False).half().to(DEV)
+    g = GPTQ(lin)
+    g.quantizer = Q.Quantizer()
+    g.quantizer.configure(4, perchannel=True, sym=False)
+    with pytest.raises(NotImplementedError):
+        g.fasterquant(lut_quant=True)
+    with pytest.raises(_lib.GptqB200Error):
+        GPTQ(nn.Linear(64, 8, bias=False))
