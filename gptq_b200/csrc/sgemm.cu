@@ -17,13 +17,14 @@ sgemm_kernel(int M, int N, int Kd, float alpha, const float* __restrict__ A, int
     __shared__ __align__(16) float Bs[2][SG_BK][SG_BN + SG_PAD];
 
     const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
-    if (mode == SG_UPPER_TILES && n0 + SG_BN - 1 < m0) return;      // tile strictly below the diagonal
+    if ((mode & SG_UPPER_TILES) && n0 + SG_BN - 1 < m0) return;     // tile strictly below the diagonal
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
 
-    int kbeg = 0;
-    if (mode == SG_A_UPPER) kbeg = (m0 / SG_BK) * SG_BK;            // op(A)[m][k] == 0 for k < m0 <= m
-    const int nk = (Kd - kbeg + SG_BK - 1) / SG_BK;
+    int kbeg = 0, kend = Kd;
+    if (mode & SG_A_UPPER) kbeg = (m0 / SG_BK) * SG_BK;             // op(A)[m][k] == 0 for k < m0 <= m
+    if (mode & SG_B_UPPER) kend = min(Kd, n0 + SG_BN);              // op(B)[k][n] == 0 for k > n
+    const int nk = kend > kbeg ? (kend - kbeg + SG_BK - 1) / SG_BK : 0;
 
     float acc[8][8];
 #pragma unroll

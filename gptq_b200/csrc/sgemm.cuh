@@ -4,10 +4,11 @@
 
 namespace gq {
 
-enum SgemmMode {
+enum SgemmMode {          // bit mask
     SG_FULL = 0,
     SG_UPPER_TILES = 1,   // C square: skip tiles that lie strictly below the diagonal
     SG_A_UPPER = 2,       // op(A) is upper triangular (op(A)[m][k] == 0 for k < m): skip leading k
+    SG_B_UPPER = 4,       // op(B) is upper triangular (op(B)[k][n] == 0 for k > n): skip trailing k
 };
 
 // C[M,N] <- alpha * op(A) op(B) + beta * C   (row-major, fp32, IEEE FMA accumulation)

@@ -4,19 +4,21 @@
 // calibration sample, full square, TF32 off.  Here: fp16/bf16 operands straight from the
 // activations, fp32 accumulation in TMEM, lower-triangular tiles only.
 //
-// Data flow per CTA (persistent, one CTA per SM, 192 threads):
+// Data flow per CTA (persistent, one CTA per SM, 320 threads):
 //   warp 0   TMA producer: X is [tokens, K] row-major, so BOTH operands of X^T X are "MN-major"
 //            (channel index contiguous).  One stage = 64 tokens: A = 2 panels, B = 4 panels of
 //            [64 tokens x 64 channels] (8 KB each, TMA box {64,64}, SWIZZLE_128B).  Tiles on the
 //            diagonal (A's channels are a subset of B's) reuse B's panels and skip the A loads.
 //   warp 1   MMA issuer: 4 x tcgen05.mma.cta_group::1.kind::f16 (M=128, N=256, K=16) per stage,
 //            accumulating into one of two 256-column TMEM buffers; tcgen05.commit frees the stage.
-//   warps 2-5 epilogue: tcgen05.ld the finished accumulator (thread = row, 32 columns at a time),
-//            H = beta*H + alpha*acc in fp32 round-to-nearest, 128-byte contiguous per thread.
+//   warps 2-9 epilogue: tcgen05.ld each finished chunk accumulator (thread = one row x 128 columns)
+//            and add it, round-to-nearest, into 128 fp32 registers; at the end of the item
+//            H = beta*H + alpha*acc with 128-byte contiguous accesses per thread.
 //            Runs while the MMA warp fills the other TMEM buffer.
-// Work item = (tile, split): the token range of a split is walked in chunks of `chunk` tokens;
-// every chunk is accumulated in TMEM and then folded into H (or into the split's partial tile),
-// which bounds the length of the tensor-core accumulation chain.  When there are fewer tiles than
+// Work item = (tile, split): the token range of a split is walked in chunks of `chunk` tokens.
+// The tensor core's fp32 accumulator truncates (measured on B200: relative error ~ 6e-8 x chain
+// length in MMAs, biased low), so a chunk is kept short (default 512 tokens = 32 MMAs) and the
+// chunks are summed in registers with IEEE round-to-nearest adds.  When there are fewer tiles than
 // SMs the token range is split across CTAs and a second kernel reduces the partials in a fixed
 // order (deterministic; no atomics).
 #include "common.cuh"
@@ -33,7 +35,7 @@ constexpr int SY_PANEL = 64 * 128;  // bytes: 64 tokens x 64 channels x 2 B
 constexpr int SY_A_BYTES = 2 * SY_PANEL;
 constexpr int SY_B_BYTES = 4 * SY_PANEL;
 constexpr int SY_STAGE_BYTES = SY_A_BYTES + SY_B_BYTES;
-constexpr int SY_THREADS = 192;
+constexpr int SY_THREADS = 320;         // TMA warp, MMA warp, 8 epilogue warps
 constexpr int SY_SMEM = SY_STAGES * SY_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct SyrkParams {
@@ -72,7 +74,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmap);
         for (int s = 0; s < SY_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull_bar[b], 1); ptx::mbar_init(&tempty_bar[b], 4); }
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull_bar[b], 1); ptx::mbar_init(&tempty_bar[b], 8); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -152,8 +154,12 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
             }
         }
     } else {
-        // ===================================================== epilogue (4 warps)
-        const int quad = warp & 3;                // TMEM lane quadrant this warp may access
+        // ===================================================== epilogue (8 warps)
+        // warp -> (TMEM lane quadrant = warp % 4, column half): thread = one row x 128 columns, kept in
+        // 128 fp32 registers across the chunks of an item (second-level accumulator, round-to-nearest).
+        const int ew = warp - 2;
+        const int quad = warp & 3;
+        const int half = ew >> 2;
         int buf = 0; uint32_t bphase[2] = {0, 0};
         const bool hvec = ((p.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.H) & 15) == 0);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -161,57 +167,63 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
             int bi, bj; decode_tile(tile, p.nbm, bi, bj);
             const int64_t t0 = (int64_t)split * p.tokens_per_split;
             const int64_t t1 = min(t0 + p.tokens_per_split, p.T);
-            const int row = bi * SY_BM + quad * 32 + lane;
-            const int col0 = bj * SY_BN;
-            float* dst; float alpha, beta0; bool vec; int rows_ok, cols_ok;
-            if (p.splits == 1) {
-                dst = p.H + (int64_t)row * p.ldh + col0; alpha = p.alpha; beta0 = p.beta; vec = hvec;
-                rows_ok = row < p.K; cols_ok = min(SY_BN, p.K - col0);
-            } else {
-                dst = p.partial + ((int64_t)split * p.n_tiles + tile) * (SY_BM * SY_BN) + (int64_t)(quad * 32 + lane) * SY_BN;
-                alpha = 1.f; beta0 = 0.f; vec = true; rows_ok = 1; cols_ok = SY_BN;
-            }
-            bool first = true;
+            float acc[128];
+#pragma unroll
+            for (int q = 0; q < 128; ++q) acc[q] = 0.f;
             for (int64_t c0 = t0; c0 < t1; c0 += p.chunk) {
                 ptx::mbar_wait(&tfull_bar[buf], bphase[buf]);
                 ptx::tc_fence_after();
-                const float beta = first ? beta0 : 1.f;
-                const uint32_t taddr = tmem_base + buf * SY_BN + ((uint32_t)(quad * 32) << 16);
-#pragma unroll 1
-                for (int cb = 0; cb < SY_BN / 32; ++cb) {
+                const uint32_t taddr = tmem_base + buf * SY_BN + half * 128 + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
                     float v[32];
                     ptx::tmem_ld_32x32(taddr + cb * 32, v);
                     ptx::tmem_ld_wait();
-                    if (rows_ok) {
-                        float* o = dst + cb * 32;
-                        const int nc = cols_ok - cb * 32;
-                        if (nc >= 32 && vec) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                float4 r;
-                                if (beta != 0.f) {
-                                    const float4 h = *reinterpret_cast<const float4*>(o + q * 4);
-                                    r.x = fmaf(alpha, v[q * 4 + 0], beta * h.x); r.y = fmaf(alpha, v[q * 4 + 1], beta * h.y);
-                                    r.z = fmaf(alpha, v[q * 4 + 2], beta * h.z); r.w = fmaf(alpha, v[q * 4 + 3], beta * h.w);
-                                } else {
-                                    r.x = alpha * v[q * 4 + 0]; r.y = alpha * v[q * 4 + 1];
-                                    r.z = alpha * v[q * 4 + 2]; r.w = alpha * v[q * 4 + 3];
-                                }
-                                *reinterpret_cast<float4*>(o + q * 4) = r;
-                            }
-                        } else if (nc > 0) {
-#pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (q < nc) o[q] = (beta != 0.f) ? fmaf(alpha, v[q], beta * o[q]) : alpha * v[q];
-                        }
-                    }
+                    for (int q = 0; q < 32; ++q) acc[cb * 32 + q] = __fadd_rn(acc[cb * 32 + q], v[q]);
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tempty_bar[buf]);
                 bphase[buf] ^= 1;
                 buf ^= 1;
-                first = false;
+            }
+            // ---- fold the item into H (or into its split's partial tile)
+            const int row = bi * SY_BM + quad * 32 + lane;
+            const int col0 = bj * SY_BN + half * 128;
+            float* dst; float alpha, beta; bool vec; int rows_ok, cols_ok;
+            if (p.splits == 1) {
+                dst = p.H + (int64_t)row * p.ldh + col0; alpha = p.alpha; beta = p.beta; vec = hvec;
+                rows_ok = row < p.K; cols_ok = min(128, p.K - col0);
+            } else {
+                dst = p.partial + ((int64_t)split * p.n_tiles + tile) * (SY_BM * SY_BN) + (int64_t)(quad * 32 + lane) * SY_BN + half * 128;
+                alpha = 1.f; beta = 0.f; vec = true; rows_ok = 1; cols_ok = 128;
+            }
+            if (rows_ok) {
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb) {
+                    float* o = dst + cb * 32;
+                    const int nc = cols_ok - cb * 32;
+                    if (nc >= 32 && vec) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 r;
+                            if (beta != 0.f) {
+                                const float4 h = *reinterpret_cast<const float4*>(o + q * 4);
+                                r.x = fmaf(alpha, acc[cb * 32 + q * 4 + 0], beta * h.x); r.y = fmaf(alpha, acc[cb * 32 + q * 4 + 1], beta * h.y);
+                                r.z = fmaf(alpha, acc[cb * 32 + q * 4 + 2], beta * h.z); r.w = fmaf(alpha, acc[cb * 32 + q * 4 + 3], beta * h.w);
+                            } else {
+                                r.x = alpha * acc[cb * 32 + q * 4 + 0]; r.y = alpha * acc[cb * 32 + q * 4 + 1];
+                                r.z = alpha * acc[cb * 32 + q * 4 + 2]; r.w = alpha * acc[cb * 32 + q * 4 + 3];
+                            }
+                            *reinterpret_cast<float4*>(o + q * 4) = r;
+                        }
+                    } else if (nc > 0) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if (q < nc) o[q] = (beta != 0.f) ? fmaf(alpha, acc[cb * 32 + q], beta * o[q]) : alpha * acc[cb * 32 + q];
+                    }
+                }
             }
         }
     }
@@ -363,7 +375,7 @@ extern "C" int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, in
     SyrkParams p;
     p.K = K; p.T = tokens; p.nbm = pl.nbm; p.n_tiles = pl.n_tiles; p.splits = pl.splits;
     p.tokens_per_split = pl.tokens_per_split;
-    int chunk = chunk_tokens > 0 ? chunk_tokens : 4096;
+    int chunk = chunk_tokens > 0 ? chunk_tokens : 512;
     chunk = ((chunk + SY_BK - 1) / SY_BK) * SY_BK;
     p.chunk = chunk;
     p.H = H; p.ldh = ldh; p.alpha = alpha; p.beta = beta;

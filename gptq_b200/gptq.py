@@ -256,8 +256,10 @@ class GPTQ:
         info = torch.zeros(1, device=dev, dtype=torch.int32)
         nws = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
         ws = torch.empty(nws, device=dev, dtype=torch.uint8)
-        _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, info.data_ptr(), ws.data_ptr(), nws, st), "hinv_upper")
-        del ws
+        U = torch.empty((Kp, Kp), **f32)
+        _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, U.data_ptr(), Kp, info.data_ptr(), ws.data_ptr(), nws, st),
+                   "hinv_upper")
+        del ws, A
 
         if not q.ready():                               # gptq.py:181-185
             q.find_params(Wp)
@@ -283,7 +285,7 @@ class GPTQ:
         loss = torch.zeros(1, device=dev, dtype=torch.float64)
         nws = lib.gptq_b200_colloop_workspace_bytes(R, K, blocksize)
         ws = torch.empty(max(nws, 16), device=dev, dtype=torch.uint8)
-        _lib.check(lib.gptq_b200_colloop(Wp.data_ptr(), R, K, K, A.data_ptr(), Kp, blocksize, groupsize, mode,
+        _lib.check(lib.gptq_b200_colloop(Wp.data_ptr(), R, K, K, U.data_ptr(), Kp, blocksize, groupsize, mode,
                                          _lib.ptr(gidx), scale.data_ptr(), zero.data_ptr(), ng, maxq, int(q.sym),
                                          int(q.mse), float(q.norm), int(q.grid), float(q.maxshrink), Q.data_ptr(), K,
                                          codes.data_ptr(), K, loss.data_ptr(), ws.data_ptr(), nws, st), "colloop")

@@ -88,14 +88,15 @@ int gptq_b200_hessian_gather(const float* H, int K, int64_t ldh, const int32_t* 
 /* ------------------------------------------------------------------------------------------
  *     Inverse-Cholesky chain.  Replaces gptq.py:177-179
  *         H = cholesky(H); H = cholesky_inverse(H); H = cholesky(H, upper=True)
- *     A (damped, [Kp,Kp], Kp % 128 == 0) is overwritten by U, the upper factor of A^-1
- *     (A^-1 = U^T U); the strict lower triangle is zeroed.  Computed as U = R^-1 with
- *     A = R R^T (R upper): one blocked backward Cholesky + one blocked triangular inverse, fp32.
+ *     A (damped, [Kp,Kp], Kp % 128 == 0, upper triangle read) is DESTROYED; U ([Kp,Kp], a separate
+ *     matrix) receives the upper factor of A^-1 (A^-1 = U^T U) with a zero strict lower triangle.
+ *     Computed as U = R^-1 with A = R R^T (R upper): blocked backward Cholesky fused with a
+ *     blocked triangular inverse in one recursion of fp32 GEMMs (chol.cu).
  *     *info (device int32): 0 ok, i+1 if the pivot at index i was not positive
  *     (torch.linalg.LinAlgError in the reference).
  * ------------------------------------------------------------------------------------------ */
 size_t gptq_b200_hinv_upper_workspace_bytes(int Kp);
-int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, int32_t* info,
+int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, float* U, int64_t ldu, int32_t* info,
                          void* ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------

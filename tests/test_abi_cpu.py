@@ -48,9 +48,9 @@ def test_abi_version_and_error_string(lib):
     assert b"argument 1" in L.gptq_b200_last_error()
     rc = L.gptq_b200_pack_codes(1, 4, 33, 33, 3, 1, 0)
     assert rc == -3
-    rc = L.gptq_b200_hinv_upper(1, 100, 100, 1, 1, 0, 0)
+    rc = L.gptq_b200_hinv_upper(1, 100, 100, 2, 100, 1, 1, 0, 0)
     assert rc == -2
-    assert L.gptq_b200_hinv_upper_workspace_bytes(256) == (2 * 128 * 128 + 256 * 128) * 4
+    assert L.gptq_b200_hinv_upper_workspace_bytes(256) == 128 * 128 * 4
     assert L.gptq_b200_colloop_workspace_bytes(1000, 4096, 128) == 1000 * 128 * 4
 
 

@@ -144,12 +144,13 @@ def _hinv_upper_gpu(H, percdamp=0.01):
     info = torch.zeros(1, dtype=torch.int32, device=DEV)
     n = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
     ws = torch.empty(n, dtype=torch.uint8, device=DEV)
-    _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, info.data_ptr(), ws.data_ptr(), n, _lib.stream()), "hinv")
+    U = torch.empty((Kp, Kp), device=DEV)
+    _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, U.data_ptr(), Kp, info.data_ptr(), ws.data_ptr(), n, _lib.stream()), "hinv")
     torch.cuda.synchronize()
-    return A[:K, :K].cpu(), int(info.item()), float(damp.item())
+    return U[:K, :K].cpu(), int(info.item()), float(damp.item())
 
 
-@pytest.mark.parametrize("K", [128, 200, 256, 640, 1024])
+@pytest.mark.parametrize("K", [128, 200, 256, 640, 1024, 1408])
 def test_hinv_upper_vs_fp64(K):
     H = _spd(K, K)
     U, info, damp = _hinv_upper_gpu(H)
@@ -305,7 +306,10 @@ def test_fasterquant_matches_reference(tag, name, golden_A, golden_B):
     dict(name="opt66b_b3_act", R=256, K=1152, bits=3, actorder=True),
 ])
 def test_fasterquant_vs_oracle_medium(cfg):
-    """The five BASELINE.json configurations at reduced width, oracle run live on the host CPU with the SAME H."""
+    """The five BASELINE.json configurations at reduced width; the oracle runs live on the host CPU.
+
+    Solver parity is asserted on IDENTICAL H (the oracle's fp32 Hessian handed to the GPU solver);
+    the end-to-end run (H from the tcgen05 syrk) is asserted against the same budget and logged."""
     R, K = cfg["R"], cfg["K"]
     g0 = torch.Generator().manual_seed(42)
     W16 = (torch.randn(R, K, generator=g0) * 0.02).half()
@@ -316,20 +320,20 @@ def test_fasterquant_vs_oracle_medium(cfg):
     qp = O.QParams(bits=cfg["bits"])
     ref = O.fasterquant(W16, st.H, qp, groupsize=cfg.get("groupsize", -1), actorder=cfg.get("actorder", False),
                         static_groups=cfg.get("static_groups", False))
-    lin, g = _run_gptq(W16, batches, cfg)
-    Hrel = None
-    mism_codes = 1.0 - O.code_agreement(g.codes.cpu(), ref.codes)
-    mism_q = float((lin.weight.data.cpu() != ref.Q.half()).double().mean())
-    rel_err = abs(g.error - ref.error) / abs(ref.error)
-    rec_gpu = O.recon_error(W16.float(), lin.weight.data.cpu().float(), st.H)
-    rec_ref = O.recon_error(W16.float(), ref.Q, st.H)
-    _log(test="fasterquant_medium", case=cfg["name"], code_mismatch=mism_codes, q_mismatch=mism_q, err_gpu=g.error,
-         err_ref=ref.error, recon_gpu=rec_gpu, recon_ref=rec_ref)
-    assert mism_codes <= 1e-3
-    assert rel_err <= 1e-2
-    assert abs(rec_gpu - rec_ref) <= 1e-2 * rec_ref
-    if cfg.get("actorder", False):
-        assert torch.equal(g.perm.cpu().long(), ref.perm)
+    for mode in ("same_H", "gpu_H"):
+        lin, g = _run_gptq(W16, batches, cfg, H_override=st.H if mode == "same_H" else None)
+        mism_codes = 1.0 - O.code_agreement(g.codes.cpu(), ref.codes)
+        mism_q = float((lin.weight.data.cpu() != ref.Q.half()).double().mean())
+        rel_err = abs(g.error - ref.error) / abs(ref.error)
+        rec_gpu = O.recon_error(W16.float(), lin.weight.data.cpu().float(), st.H)
+        rec_ref = O.recon_error(W16.float(), ref.Q, st.H)
+        _log(test="fasterquant_medium", case=cfg["name"], H=mode, code_mismatch=mism_codes, q_mismatch=mism_q,
+             err_gpu=g.error, err_ref=ref.error, recon_gpu=rec_gpu, recon_ref=rec_ref)
+        assert mism_codes <= 1e-3, mode
+        assert rel_err <= 1e-2, mode
+        assert abs(rec_gpu - rec_ref) <= 1e-2 * rec_ref, mode
+        if cfg.get("actorder", False) and mode == "same_H":
+            assert torch.equal(g.perm.cpu().long(), ref.perm)
 
 
 def test_fasterquant_not_pd_raises():
