@@ -10,9 +10,8 @@
 // square GEMMs (see hinv_rec below) instead of 128-wide panels.
 // SURVEY Appendix B measured 0 code mismatches for this route against the reference.
 //
-// Block size 128.  Diagonal blocks are factored AND inverted by one CTA in shared memory
-// (4 lanes per matrix row, warp shuffles for the dot-product reductions); panels and trailing
-// updates are fp32 GEMMs (sgemm.cu).
+// Block size 128.  Diagonal blocks are factored AND inverted by one CTA with one matrix row per
+// 8x8 register tile per thread (256 threads); everything else is fp32 GEMMs (sgemm.cu).
 #include "sgemm.cuh"
 
 namespace gq {
@@ -20,69 +19,151 @@ namespace gq {
 constexpr int CB = 128;            // block size
 constexpr int CP = CB + 1;         // smem pitch (conflict-free row-per-thread access)
 
-// A_jj (upper triangle read) -> R_jj in place (strict lower zeroed), Dinv = R_jj^-1 (dense 128x128,
-// strict lower zero).  512 threads: thread (i = tid/4, q = tid%4) owns a quarter of row i's dots.
-__global__ void __launch_bounds__(512)
-chol_diag_kernel(float* __restrict__ Ablk, int64_t lda, float* __restrict__ Dinv, int64_t ldd, int32_t* __restrict__ info, int base_index) {
-    extern __shared__ float sm[];
-    float* S = sm;                 // [128][129]  A -> R
-    float* X = sm + CB * CP;       // [128][129]  R^-1
+// A_jj (upper triangle read) -> Dinv = R_jj^-1 (dense 128x128, strict lower zero), A_jj = R_jj R_jj^T.
+//
+// 256 threads as a 16x16 grid; thread (ty,tx) owns the 8x8 cyclic sub-matrix
+//     rows a*16+ty, cols b*16+tx  (a,b = 0..7)
+// of the 128x128 block IN REGISTERS, so each of the 128 sequential steps is one rank-1 update of a
+// register tile: the pivot column (and, for the inverse, the pivot row) is broadcast through a
+// 128-float shared-memory vector, two block barriers per step.  The step loop is written as
+// (outer block index, statically unrolled) x (inner 16, rolled) so every register index is static
+// and tiles that lie outside the still-active triangle are skipped at compile time.
+//   phase 1: right-looking backward Cholesky  A = R R^T  (columns 127 .. 0)
+//   phase 2: X = R^-1 by forward column elimination of  X R = I  (columns 0 .. 127)
+template <int JB>
+__device__ __forceinline__ void chol_phase1_block(float (&r)[8][8], float* colb, float* s_piv, int32_t* info, int base_index,
+                                                  int tx, int ty) {
+#pragma unroll 1
+    for (int jt = 15; jt >= 0; --jt) {
+        const int j = JB * 16 + jt;
+        const float piv = *s_piv;
+        if (tx == jt) {                                  // owners of column j: rows a*16+ty, a <= JB
+#pragma unroll
+            for (int a = 0; a <= JB; ++a) {
+                const int row = a * 16 + ty;
+                float c = (row == j) ? piv : __fdiv_rn(r[a][JB], piv);
+                if (row > j) c = 0.f;
+                r[a][JB] = c;
+                colb[row] = c;
+            }
+        }
+        __syncthreads();
+        float cr[JB + 1], cc[JB + 1];
+#pragma unroll
+        for (int a = 0; a <= JB; ++a) cr[a] = colb[a * 16 + ty];
+#pragma unroll
+        for (int b = 0; b <= JB; ++b) cc[b] = colb[b * 16 + tx];
+#pragma unroll
+        for (int a = 0; a <= JB; ++a)
+#pragma unroll
+            for (int b = 0; b <= JB; ++b) {
+                const bool act = (a < JB || ty < jt) && (b < JB || tx < jt);     // row < j && col < j
+                if (act) r[a][b] = fmaf(-cr[a], cc[b], r[a][b]);
+            }
+        // next pivot: element (j-1, j-1) is final now
+        if (j > 0) {
+            const int pj = j - 1;
+            if (tx == (pj & 15) && ty == (pj & 15)) {
+                const float v = (jt > 0) ? r[JB][JB] : r[JB > 0 ? JB - 1 : 0][JB > 0 ? JB - 1 : 0];
+                if (!(v > 0.f)) atomicCAS(info, 0, base_index + pj + 1);
+                *s_piv = sqrtf(v);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <int CBI>
+__device__ __forceinline__ void chol_phase2_block(const float (&r)[8][8], float (&x)[8][8], float* colb2, float* rowb2, int tx, int ty) {
+#pragma unroll 1
+    for (int ct = 0; ct < 16; ++ct) {
+        const int c = CBI * 16 + ct;
+        float* rowb = rowb2 + (ct & 1) * CB;             // double-buffered: no trailing barrier needed
+        float* colb = colb2 + (ct & 1) * CB;
+        if (ty == ct) {                                  // owners of row c of R: cols b*16+tx, b >= CBI
+#pragma unroll
+            for (int b = CBI; b < 8; ++b) rowb[b * 16 + tx] = r[CBI][b];
+        }
+        __syncthreads();
+        const float d = rowb[c];
+        if (tx == ct) {                                  // owners of column c of X: rows a*16+ty, a <= CBI
+#pragma unroll
+            for (int a = 0; a <= CBI; ++a) {
+                const float v = __fdiv_rn(x[a][CBI], d);
+                x[a][CBI] = v;
+                colb[a * 16 + ty] = v;
+            }
+        }
+        __syncthreads();
+        float xc[CBI + 1], rr[8];
+#pragma unroll
+        for (int a = 0; a <= CBI; ++a) xc[a] = colb[a * 16 + ty];
+#pragma unroll
+        for (int b = CBI; b < 8; ++b) rr[b] = rowb[b * 16 + tx];
+#pragma unroll
+        for (int a = 0; a <= CBI; ++a)
+#pragma unroll
+            for (int b = CBI; b < 8; ++b) {
+                const bool act = (a < CBI || ty <= ct) && (b > CBI || tx > ct);    // row <= c && col > c
+                if (act) x[a][b] = fmaf(-xc[a], rr[b], x[a][b]);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict__ Dinv, int64_t ldd,
+                 int32_t* __restrict__ info, int base_index) {
+    __shared__ float colb[2 * CB];
+    __shared__ float rowb[2 * CB];
     __shared__ float s_piv;
-    const int tid = threadIdx.x;
-    const int i = tid >> 2, q = tid & 3;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
-    for (int idx = tid; idx < CB * CB; idx += 512) {
-        int r = idx >> 7, c = idx & 127;
-        S[r * CP + c] = (c >= r) ? Ablk[(int64_t)r * lda + c] : 0.f;
-        X[r * CP + c] = 0.f;
+    float r[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int row = a * 16 + ty, col = b * 16 + tx;
+            r[a][b] = (col >= row) ? Ablk[(int64_t)row * lda + col] : 0.f;
+        }
+    if (tx == 15 && ty == 15) {
+        const float v = r[7][7];
+        if (!(v > 0.f)) atomicCAS(info, 0, base_index + CB);
+        s_piv = sqrtf(v);
     }
     __syncthreads();
 
-    // ---- backward Cholesky, left-looking: column j uses columns k > j.
-    for (int j = CB - 1; j >= 0; --j) {
-        float s = 0.f;
-        if (i <= j) {
-            const float* ri = S + i * CP;
-            const float* rj = S + j * CP;
-            for (int k = j + 1 + q; k < CB; k += 4) s = fmaf(ri[k], rj[k], s);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        float v = 0.f;
-        if (i <= j) v = S[i * CP + j] - s;
-        if (i == j && q == 0) {
-            if (!(v > 0.f)) { if (atomicCAS(info, 0, base_index + j + 1) == 0) {} }
-            s_piv = sqrtf(v);
-        }
-        __syncthreads();
-        if (i <= j && q == 0) S[i * CP + j] = (i == j) ? s_piv : __fdiv_rn(v, s_piv);
-        __syncthreads();
-    }
+    // ---------------- phase 1: for j = 127..0: scale column j, rank-1 update of the leading j x j block
+    chol_phase1_block<7>(r, colb, &s_piv, info, base_index, tx, ty);
+    chol_phase1_block<6>(r, colb, &s_piv, info, base_index, tx, ty);
+    chol_phase1_block<5>(r, colb, &s_piv, info, base_index, tx, ty);
+    chol_phase1_block<4>(r, colb, &s_piv, info, base_index, tx, ty);
+    chol_phase1_block<3>(r, colb, &s_piv, info, base_index, tx, ty);
+    chol_phase1_block<2>(r, colb, &s_piv, info, base_index, tx, ty);
+    chol_phase1_block<1>(r, colb, &s_piv, info, base_index, tx, ty);
+    chol_phase1_block<0>(r, colb, &s_piv, info, base_index, tx, ty);
 
-    // ---- X = R^-1, row i independent: X[i][c] = -(sum_{k=i}^{c-1} X[i][k] R[k][c]) / R[c][c]
-    {
-        float* xi = X + i * CP;
-        if (q == 0) xi[i] = __fdiv_rn(1.f, S[i * CP + i]);
-        __syncwarp();
-        // warp-uniform trip count (a warp holds rows i0..i0+7): lanes whose row starts later idle
-        const int i0 = (tid >> 5) * 8;
-        for (int c = i0 + 1; c < CB; ++c) {
-            const bool active = c > i;
-            float s = 0.f;
-            if (active)
-                for (int k = i + q; k < c; k += 4) s = fmaf(xi[k], S[k * CP + c], s);
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            if (active && q == 0) xi[c] = __fdiv_rn(-s, S[c * CP + c]);
-            __syncwarp();
+    // ---------------- phase 2: x = I; for c = 0..127: x[:,c] /= R[c][c]; x[:,c'] -= x[:,c] R[c][c'] (c' > c)
+    float x[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) x[a][b] = (a == b && tx == ty) ? 1.f : 0.f;
+    chol_phase2_block<0>(r, x, colb, rowb, tx, ty);
+    chol_phase2_block<1>(r, x, colb, rowb, tx, ty);
+    chol_phase2_block<2>(r, x, colb, rowb, tx, ty);
+    chol_phase2_block<3>(r, x, colb, rowb, tx, ty);
+    chol_phase2_block<4>(r, x, colb, rowb, tx, ty);
+    chol_phase2_block<5>(r, x, colb, rowb, tx, ty);
+    chol_phase2_block<6>(r, x, colb, rowb, tx, ty);
+    chol_phase2_block<7>(r, x, colb, rowb, tx, ty);
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int row = a * 16 + ty, col = b * 16 + tx;
+            Dinv[(int64_t)row * ldd + col] = (col >= row) ? x[a][b] : 0.f;
         }
-    }
-    __syncthreads();
-    for (int idx = tid; idx < CB * CB; idx += 512) {
-        int r = idx >> 7, c = idx & 127;
-        Ablk[(int64_t)r * lda + c] = S[r * CP + c];
-        Dinv[(int64_t)r * ldd + c] = X[r * CP + c];
-    }
 }
 
 // ------------------------------------------------------------------ recursive driver
@@ -104,7 +185,7 @@ static void hinv_rec(HinvCtx& c, int a, int b) {
     if (c.rc) return;
     if (b - a == 1) {
         const int c0 = a * CB;
-        chol_diag_kernel<<<1, 512, c.smem, c.st>>>(c.A + (int64_t)c0 * c.lda + c0, c.lda, c.V + (int64_t)c0 * c.ldv + c0,
+        chol_diag_kernel<<<1, 256, 0, c.st>>>(c.A + (int64_t)c0 * c.lda + c0, c.lda, c.V + (int64_t)c0 * c.ldv + c0,
                                                    c.ldv, c.info, c0);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return;
@@ -156,12 +237,7 @@ extern "C" int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, float* U, int
     GQ_ARG(info, 6, "null"); GQ_ARG(ws, 7, "null");
     GQ_ARG(ws_bytes >= gptq_b200_hinv_upper_workspace_bytes(Kp), 8, "workspace too small");
     cudaStream_t st = as_stream(stream);
-    const size_t smem = 2 * CB * CP * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        GQ_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    const size_t smem = 0;
     GQ_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     GQ_CUDA(cudaMemset2DAsync(U, ldu * sizeof(float), 0, (size_t)Kp * sizeof(float), Kp, st));
     HinvCtx c{A, lda, U, ldu, static_cast<float*>(ws), info, st, smem, 0};

@@ -49,8 +49,38 @@ STAGE_SAMPLES = int(os.environ.get("GPTQ_B200_STAGE_SAMPLES", "16"))
 CHUNK_TOKENS = int(os.environ.get("GPTQ_B200_CHUNK_TOKENS", "0"))     # 0 = library default
 
 
+# Optional per-call device timing: set ``gptq_b200.gptq.PROFILE = []`` and every C-ABI hot call appends
+# (name, start_event, end_event, work) recorded on the launching stream (bench.py reads it after a sync).
+PROFILE = None
+
+
+class _prof:
+    def __init__(self, name, work=0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record()
+            PROFILE.append((self.name, self.a, self.b, self.work))
+        return False
+
+
 def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
+
+
+def syrk_issued_flops(K: int, tokens: int) -> float:
+    """MMA flops the syrk kernel actually issues: 128x256 tiles touching the lower triangle."""
+    nbm, nbn = (K + 127) // 128, (K + 255) // 256
+    tiles = sum(nbm - 2 * j for j in range(nbn))
+    return 2.0 * tiles * 128 * 256 * tokens
 
 
 class GPTQ:
@@ -141,9 +171,10 @@ class GPTQ:
         need = lib.gptq_b200_syrk_workspace_bytes(K, self._staged)
         if need and (self._ws is None or self._ws.numel() < need):
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        _lib.check(lib.gptq_b200_syrk_accum(self._stage.data_ptr(), _lib.dt(self._stage), self._staged, K,
-                                            self._stage.stride(0), self._S.data_ptr(), K, 1.0, 1.0, CHUNK_TOKENS,
-                                            _lib.ptr(self._ws) if need else 0, need, _lib.stream()), "syrk_accum")
+        with _prof("syrk", syrk_issued_flops(K, self._staged)):
+            _lib.check(lib.gptq_b200_syrk_accum(self._stage.data_ptr(), _lib.dt(self._stage), self._staged, K,
+                                                self._stage.stride(0), self._S.data_ptr(), K, 1.0, 1.0, CHUNK_TOKENS,
+                                                _lib.ptr(self._ws) if need else 0, need, _lib.stream()), "syrk_accum")
         self._staged = 0
 
     @property
@@ -215,6 +246,7 @@ class GPTQ:
         self._H = None
         self._S = None
         self._stage = None
+        self._last = None
         if H is None:
             raise RuntimeError("fasterquant: H was already consumed or freed")
 
@@ -257,8 +289,9 @@ class GPTQ:
         nws = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
         ws = torch.empty(nws, device=dev, dtype=torch.uint8)
         U = torch.empty((Kp, Kp), **f32)
-        _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, U.data_ptr(), Kp, info.data_ptr(), ws.data_ptr(), nws, st),
-                   "hinv_upper")
+        with _prof("hinv_upper", 2.0 / 3.0 * Kp ** 3):
+            _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, U.data_ptr(), Kp, info.data_ptr(), ws.data_ptr(), nws,
+                                                st), "hinv_upper")
         del ws, A
 
         if not q.ready():                               # gptq.py:181-185
@@ -285,10 +318,12 @@ class GPTQ:
         loss = torch.zeros(1, device=dev, dtype=torch.float64)
         nws = lib.gptq_b200_colloop_workspace_bytes(R, K, blocksize)
         ws = torch.empty(max(nws, 16), device=dev, dtype=torch.uint8)
-        _lib.check(lib.gptq_b200_colloop(Wp.data_ptr(), R, K, K, U.data_ptr(), Kp, blocksize, groupsize, mode,
-                                         _lib.ptr(gidx), scale.data_ptr(), zero.data_ptr(), ng, maxq, int(q.sym),
-                                         int(q.mse), float(q.norm), int(q.grid), float(q.maxshrink), Q.data_ptr(), K,
-                                         codes.data_ptr(), K, loss.data_ptr(), ws.data_ptr(), nws, st), "colloop")
+        # algorithmic bytes of the column loop: W fp16 in, U upper fp32, Q fp16 + codes out
+        with _prof("colloop", 2.0 * R * K + 2.0 * K * (K + 1) + 2.0 * R * K + R * K + 8.0 * R * ng):
+            _lib.check(lib.gptq_b200_colloop(Wp.data_ptr(), R, K, K, U.data_ptr(), Kp, blocksize, groupsize, mode,
+                                             _lib.ptr(gidx), scale.data_ptr(), zero.data_ptr(), ng, maxq, int(q.sym),
+                                             int(q.mse), float(q.norm), int(q.grid), float(q.maxshrink), Q.data_ptr(), K,
+                                             codes.data_ptr(), K, loss.data_ptr(), ws.data_ptr(), nws, st), "colloop")
 
         # gptq.py:300-305: un-permute and write back in the layer's dtype
         wdtype = self.layer.weight.data.dtype
