@@ -321,12 +321,16 @@ def run_ours(args):
         "hinv_upper": {"bound": "fp32", "achieved": hv[1] / (hv[0] / 1e3) / 1e12, "unit": "TFLOP/s (2/3 K^3 useful)",
                        "share_of_step": hv[0] / ms},
     }
+    phase_ms = {k: v[0] / args.steps for k, v in agg.items()}
+    phase_ms["unattributed (staging copies, pack, allocator, host gaps)"] = ms_step - sum(phase_ms.values())
     del acts, weights
     torch.cuda.empty_cache()
 
     # ---- end-to-end run: host buffers, H2D/D2H inside the timed region
     e2e = None
     try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
         acts_h, weights_h = make_inputs(dev, rank, world, host=True)
         h2d = sum(x.numel() * 2 for x in acts_h) + sum(w.numel() * 2 for w in weights_h)
         e_steps = max(1, min(args.steps, 3))
@@ -341,7 +345,7 @@ def run_ours(args):
         out = base_line(args, value, ms_step)
         out.update({"whole_model_seconds": ms_step * N_LAYERS / 1e3, "wall_seconds_timed_region": wall,
                     "hessian_tflops_issued": syrk_tflops, "hessian_tflops_dense_equivalent": dense_equiv,
-                    "roofline": roofline, "rooflines_other": others, "clocks": clocks, "e2e": e2e,
+                    "roofline": roofline, "rooflines_other": others, "phase_ms_per_step": phase_ms, "clocks": clocks, "e2e": e2e,
                     "gpu_launches": launches, "impl": "ours"})
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_reference_sample()
@@ -360,6 +364,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -47,6 +47,7 @@ torch.backends.cudnn.allow_tf32 = False
 
 STAGE_SAMPLES = int(os.environ.get("GPTQ_B200_STAGE_SAMPLES", "16"))
 CHUNK_TOKENS = int(os.environ.get("GPTQ_B200_CHUNK_TOKENS", "0"))     # 0 = library default
+EMPTY_CACHE_ON_FREE = os.environ.get("GPTQ_B200_EMPTY_CACHE", "0") == "1"
 
 
 # Optional per-call device timing: set ``gptq_b200.gptq.PROFILE = []`` and every C-ABI hot call appends
@@ -242,7 +243,14 @@ class GPTQ:
             raise RuntimeError("Quantizer.configure() was not called")
 
         tick = time.time()
-        H = self.H                                      # materialise; consumed below (gptq.py:141-142)
+        if self._H is None and self._S is not None:     # consume the accumulator in place (no clone)
+            self._flush()
+            H = self._S
+            _lib.check(lib.gptq_b200_symmetrize(H.data_ptr(), K, K, st), "symmetrize")
+            if self.nsamples > 0:
+                H.mul_(2.0 / self.nsamples)
+        else:
+            H = self._H                                 # a user-provided / already materialised H (gptq.py:141-142)
         self._H = None
         self._S = None
         self._stage = None
@@ -251,6 +259,8 @@ class GPTQ:
             raise RuntimeError("fasterquant: H was already consumed or freed")
 
         f32 = dict(device=dev, dtype=torch.float32)
+        _p0 = _prof("prologue")
+        _p0.__enter__()
         dead = torch.empty(K, device=dev, dtype=torch.uint8)
         diag = torch.empty(K, **f32)
         damp = torch.empty(1, **f32)
@@ -285,6 +295,7 @@ class GPTQ:
         _lib.check(lib.gptq_b200_hessian_gather(H.data_ptr(), K, K, _lib.ptr(perm), damp.data_ptr(), A.data_ptr(), Kp, Kp,
                                                 st), "hessian_gather")
         del H
+        _p0.__exit__()
         info = torch.zeros(1, device=dev, dtype=torch.int32)
         nws = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
         ws = torch.empty(nws, device=dev, dtype=torch.uint8)
@@ -329,8 +340,9 @@ class GPTQ:
         wdtype = self.layer.weight.data.dtype
         Wout = torch.empty((R, K), device=dev, dtype=wdtype)
         codes_out = torch.empty((R, K), device=dev, dtype=torch.uint8)
-        _lib.check(lib.gptq_b200_finalize(Q.data_ptr(), K, codes.data_ptr(), K, R, K, _lib.ptr(invperm), Wout.data_ptr(),
-                                          _lib.dt(Wout), K, codes_out.data_ptr(), K, st), "finalize")
+        with _prof("epilogue", 4.0 * R * K + R * K + 2.0 * R * K + R * K):
+            _lib.check(lib.gptq_b200_finalize(Q.data_ptr(), K, codes.data_ptr(), K, R, K, _lib.ptr(invperm), Wout.data_ptr(),
+                                              _lib.dt(Wout), K, codes_out.data_ptr(), K, st), "finalize")
 
         torch.cuda.synchronize()                        # gptq.py:292
         bad = int(info.item())
@@ -378,4 +390,7 @@ class GPTQ:
         self._last = None
         self.Losses = None
         self.Trace = None
-        torch.cuda.empty_cache()
+        # The reference calls torch.cuda.empty_cache() here (gptq.py:318), which forces a cudaFree/cudaMalloc
+        # round trip (and a device sync) for every linear; the caching allocator makes it unnecessary.
+        if EMPTY_CACHE_ON_FREE:
+            torch.cuda.empty_cache()
