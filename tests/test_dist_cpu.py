@@ -1,0 +1,77 @@
+"""Host-side multi-GPU logic on CPU: partition arithmetic and the two exchanges (gloo, world size 2)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gptq_b200 import dist as gd
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 768, 4096, 11008, 12288):
+        for world in (1, 2, 3, 4, 8):
+            for align in (1, 16):
+                spans = [gd.shard_range(n, r, world, align) for r in range(world)]
+                assert spans[0][0] == 0 and spans[-1][1] == n
+                for (a, b), (c, d) in zip(spans, spans[1:]):
+                    assert b == c and a <= b
+                sizes = [b - a for a, b in spans]
+                assert max(sizes) - min(sizes) <= align
+                if align > 1:
+                    assert all(a % align == 0 for a, b in spans if b > a)
+
+
+def test_sample_shard_covers_all_samples():
+    for world in (1, 2, 4, 8):
+        seen = sorted(j for r in range(world) for j in gd.sample_shard(128, r, world))
+        assert seen == list(range(128))
+
+
+class _FakeGPTQ:
+    def __init__(self, S, n):
+        self._S, self.nsamples = S, n
+
+    def raw_accumulator(self):
+        return self._S
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, rows):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # exchange #1: partial Hessians + sample counts
+        g = torch.Generator().manual_seed(rank)
+        X = torch.randn(64, 16, generator=g)
+        fake = _FakeGPTQ(X.t() @ X, 64 // 2 + rank)
+        gd.allreduce_hessian(fake)
+        want = sum((torch.randn(64, 16, generator=torch.Generator().manual_seed(r)).t()
+                    @ torch.randn(64, 16, generator=torch.Generator().manual_seed(r))) for r in range(world))
+        assert torch.allclose(fake._S, want, atol=1e-5)
+        assert fake.nsamples == sum(64 // 2 + r for r in range(world))
+        # exchange #2: row shards (uneven on purpose)
+        full = torch.arange(rows * 5, dtype=torch.float32).reshape(rows, 5)
+        lo, hi = gd.shard_range(rows, rank, world)
+        got = gd.allgather_rows(full[lo:hi].clone(), rows)
+        assert torch.equal(got, full)
+        codes = (torch.arange(rows * 8) % 251).to(torch.uint8).reshape(rows, 8)
+        assert torch.equal(gd.allgather_rows(codes[lo:hi].clone(), rows), codes)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("rows", [8, 11])
+def test_exchanges_world2_gloo(rows):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, rows), nprocs=2, join=True)
