@@ -30,18 +30,24 @@ constexpr int CP = CB + 1;         // smem pitch (conflict-free row-per-thread a
 // and tiles that lie outside the still-active triangle are skipped at compile time.
 //   phase 1: right-looking backward Cholesky  A = R R^T  (columns 127 .. 0)
 //   phase 2: X = R^-1 by forward column elimination of  X R = I  (columns 0 .. 127)
+// 1/sqrt(v): MUFU.RSQ + one Newton step (error < 1 ulp; nothing downstream is bit-matched to LAPACK)
+__device__ __forceinline__ float inv_sqrt(float v) {
+    float y = rsqrtf(v);
+    return y * fmaf(-0.5f * v, y * y, 1.5f);
+}
+
 template <int JB>
-__device__ __forceinline__ void chol_phase1_block(float (&r)[8][8], float* colb, float* s_piv, int32_t* info, int base_index,
+__device__ __forceinline__ void chol_phase1_block(float (&r)[8][8], float* colb, float* rd, int32_t* info, int base_index,
                                                   int tx, int ty) {
 #pragma unroll 1
     for (int jt = 15; jt >= 0; --jt) {
         const int j = JB * 16 + jt;
-        const float piv = *s_piv;
+        const float rinv = rd[j];                        // 1 / R[j][j], published by the pivot owner
         if (tx == jt) {                                  // owners of column j: rows a*16+ty, a <= JB
 #pragma unroll
             for (int a = 0; a <= JB; ++a) {
                 const int row = a * 16 + ty;
-                float c = (row == j) ? piv : __fdiv_rn(r[a][JB], piv);
+                float c = r[a][JB] * rinv;               // row == j: v * rsqrt(v) = sqrt(v)
                 if (row > j) c = 0.f;
                 r[a][JB] = c;
                 colb[row] = c;
@@ -66,7 +72,7 @@ __device__ __forceinline__ void chol_phase1_block(float (&r)[8][8], float* colb,
             if (tx == (pj & 15) && ty == (pj & 15)) {
                 const float v = (jt > 0) ? r[JB][JB] : r[JB > 0 ? JB - 1 : 0][JB > 0 ? JB - 1 : 0];
                 if (!(v > 0.f)) atomicCAS(info, 0, base_index + pj + 1);
-                *s_piv = sqrtf(v);
+                rd[pj] = inv_sqrt(v);
             }
         }
         __syncthreads();
@@ -74,7 +80,8 @@ __device__ __forceinline__ void chol_phase1_block(float (&r)[8][8], float* colb,
 }
 
 template <int CBI>
-__device__ __forceinline__ void chol_phase2_block(const float (&r)[8][8], float (&x)[8][8], float* colb2, float* rowb2, int tx, int ty) {
+__device__ __forceinline__ void chol_phase2_block(const float (&r)[8][8], float (&x)[8][8], float* colb2, float* rowb2,
+                                                  const float* rd, int tx, int ty) {
 #pragma unroll 1
     for (int ct = 0; ct < 16; ++ct) {
         const int c = CBI * 16 + ct;
@@ -85,11 +92,11 @@ __device__ __forceinline__ void chol_phase2_block(const float (&r)[8][8], float 
             for (int b = CBI; b < 8; ++b) rowb[b * 16 + tx] = r[CBI][b];
         }
         __syncthreads();
-        const float d = rowb[c];
+        const float dinv = rd[c];                        // 1 / R[c][c] from phase 1
         if (tx == ct) {                                  // owners of column c of X: rows a*16+ty, a <= CBI
 #pragma unroll
             for (int a = 0; a <= CBI; ++a) {
-                const float v = __fdiv_rn(x[a][CBI], d);
+                const float v = x[a][CBI] * dinv;
                 x[a][CBI] = v;
                 colb[a * 16 + ty] = v;
             }
@@ -115,7 +122,7 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
                  int32_t* __restrict__ info, int base_index) {
     __shared__ float colb[2 * CB];
     __shared__ float rowb[2 * CB];
-    __shared__ float s_piv;
+    __shared__ float rd[CB];                             // 1 / R[j][j]
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 
     float r[8][8];
@@ -129,19 +136,19 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
     if (tx == 15 && ty == 15) {
         const float v = r[7][7];
         if (!(v > 0.f)) atomicCAS(info, 0, base_index + CB);
-        s_piv = sqrtf(v);
+        rd[CB - 1] = inv_sqrt(v);
     }
     __syncthreads();
 
     // ---------------- phase 1: for j = 127..0: scale column j, rank-1 update of the leading j x j block
-    chol_phase1_block<7>(r, colb, &s_piv, info, base_index, tx, ty);
-    chol_phase1_block<6>(r, colb, &s_piv, info, base_index, tx, ty);
-    chol_phase1_block<5>(r, colb, &s_piv, info, base_index, tx, ty);
-    chol_phase1_block<4>(r, colb, &s_piv, info, base_index, tx, ty);
-    chol_phase1_block<3>(r, colb, &s_piv, info, base_index, tx, ty);
-    chol_phase1_block<2>(r, colb, &s_piv, info, base_index, tx, ty);
-    chol_phase1_block<1>(r, colb, &s_piv, info, base_index, tx, ty);
-    chol_phase1_block<0>(r, colb, &s_piv, info, base_index, tx, ty);
+    chol_phase1_block<7>(r, colb, rd, info, base_index, tx, ty);
+    chol_phase1_block<6>(r, colb, rd, info, base_index, tx, ty);
+    chol_phase1_block<5>(r, colb, rd, info, base_index, tx, ty);
+    chol_phase1_block<4>(r, colb, rd, info, base_index, tx, ty);
+    chol_phase1_block<3>(r, colb, rd, info, base_index, tx, ty);
+    chol_phase1_block<2>(r, colb, rd, info, base_index, tx, ty);
+    chol_phase1_block<1>(r, colb, rd, info, base_index, tx, ty);
+    chol_phase1_block<0>(r, colb, rd, info, base_index, tx, ty);
 
     // ---------------- phase 2: x = I; for c = 0..127: x[:,c] /= R[c][c]; x[:,c'] -= x[:,c] R[c][c'] (c' > c)
     float x[8][8];
@@ -149,14 +156,14 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
     for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 8; ++b) x[a][b] = (a == b && tx == ty) ? 1.f : 0.f;
-    chol_phase2_block<0>(r, x, colb, rowb, tx, ty);
-    chol_phase2_block<1>(r, x, colb, rowb, tx, ty);
-    chol_phase2_block<2>(r, x, colb, rowb, tx, ty);
-    chol_phase2_block<3>(r, x, colb, rowb, tx, ty);
-    chol_phase2_block<4>(r, x, colb, rowb, tx, ty);
-    chol_phase2_block<5>(r, x, colb, rowb, tx, ty);
-    chol_phase2_block<6>(r, x, colb, rowb, tx, ty);
-    chol_phase2_block<7>(r, x, colb, rowb, tx, ty);
+    chol_phase2_block<0>(r, x, colb, rowb, rd, tx, ty);
+    chol_phase2_block<1>(r, x, colb, rowb, rd, tx, ty);
+    chol_phase2_block<2>(r, x, colb, rowb, rd, tx, ty);
+    chol_phase2_block<3>(r, x, colb, rowb, rd, tx, ty);
+    chol_phase2_block<4>(r, x, colb, rowb, rd, tx, ty);
+    chol_phase2_block<5>(r, x, colb, rowb, rd, tx, ty);
+    chol_phase2_block<6>(r, x, colb, rowb, rd, tx, ty);
+    chol_phase2_block<7>(r, x, colb, rowb, rd, tx, ty);
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -202,18 +209,18 @@ static void hinv_rec(HinvCtx& c, int a, int b) {
     hinv_rec(c, m, b);
     if (c.rc) return;
     // Tt[n2 x n1] = V22[n2 x n2] * A12^T
-    c.rc = sgemm_launch(0, 1, n2, n1, n2, 1.f, V22, c.ldv, A12, c.lda, 0.f, Tt, c.lda, SG_A_UPPER, c.st);
+    c.rc = gemm_fp32(0, 1, n2, n1, n2, 1.f, V22, c.ldv, A12, c.lda, 0.f, Tt, c.lda, SG_A_UPPER, c.st);
     if (c.rc) return;
     // A11 -= Tt^T Tt
-    c.rc = sgemm_launch(1, 0, n1, n1, n2, -1.f, Tt, c.lda, Tt, c.lda, 1.f, A11, c.lda, SG_UPPER_TILES, c.st);
+    c.rc = gemm_fp32(1, 0, n1, n1, n2, -1.f, Tt, c.lda, Tt, c.lda, 1.f, A11, c.lda, SG_UPPER_TILES, c.st);
     if (c.rc) return;
     hinv_rec(c, a, m);
     if (c.rc) return;
     // S[n1 x n2] = V11 * Tt^T
-    c.rc = sgemm_launch(0, 1, n1, n2, n1, 1.f, V11, c.ldv, Tt, c.lda, 0.f, c.S, n2, SG_A_UPPER, c.st);
+    c.rc = gemm_fp32(0, 1, n1, n2, n1, 1.f, V11, c.ldv, Tt, c.lda, 0.f, c.S, n2, SG_A_UPPER, c.st);
     if (c.rc) return;
     // V12 = -S * V22
-    c.rc = sgemm_launch(0, 0, n1, n2, n2, -1.f, c.S, n2, V22, c.ldv, 0.f, V12, c.ldv, SG_B_UPPER, c.st);
+    c.rc = gemm_fp32(0, 0, n1, n2, n2, -1.f, c.S, n2, V22, c.ldv, 0.f, V12, c.ldv, SG_B_UPPER, c.st);
 }
 
 }  // namespace gq

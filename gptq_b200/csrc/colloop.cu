@@ -23,11 +23,12 @@ constexpr int BQ_ROWS = 16;
 constexpr int BQ_THREADS = 128;
 constexpr int BQ_B = 128;            // max block width handled by the kernel
 constexpr int BQ_SP = BQ_B + 1;      // pitch of the scale/zero tiles
+constexpr int BQ_SUPER = 4;          // blocks per super-block of the two-level lazy update
 
 struct BQArgs {
     float* W; int R; int K; int64_t ldw; const float* U; int64_t ldu; int i1; int count;
     const int32_t* gidx; const float* scale; const float* zero; int ng; float maxq; int trits;
-    float* Q; int64_t ldq; uint8_t* codes; int64_t ldc; float* Err; double* loss;
+    float* Q; int64_t ldq; uint8_t* codes; int64_t ldc; float* Err; int64_t lde; double* loss;
 };
 
 __global__ void __launch_bounds__(BQ_THREADS)
@@ -118,7 +119,7 @@ blockquant_kernel(BQArgs a) {
                     else { code = quant_code(wi, sc, zr, a.maxq); q = dequant(code, sc, zr); }
                     const float diff = __fsub_rn(wi, q);
                     const float err = __fdiv_rn(diff, d);                  // gptq.py:269
-                    loss += (double)__fdiv_rn(__fmul_rn(diff, diff), __fmul_rn(d, d));   // gptq.py:267
+                    loss += (double)__fmul_rn(err, err);      // gptq.py:267: (w-q)^2/d^2 == err^2 up to one rounding (reported scalar only)
                     // rank-1 update of the columns this lane still owns (gptq.py:270)
 #pragma unroll
                     for (int k2 = kk; k2 < 4; ++k2) {
@@ -150,7 +151,7 @@ blockquant_kernel(BQArgs a) {
             if (c >= count) continue;
             float* qp = a.Q + (int64_t)row * a.ldq + i1 + c;
             uint8_t* cp = a.codes + (int64_t)row * a.ldc + i1 + c;
-            float* ep = a.Err + (int64_t)row * BQ_B + c;
+            float* ep = a.Err + (int64_t)row * a.lde + c;
             if (c + 3 < count) {
                 if (qvec) *reinterpret_cast<float4*>(qp) = make_float4(qv[kk * 4], qv[kk * 4 + 1], qv[kk * 4 + 2], qv[kk * 4 + 3]);
                 else { qp[0] = qv[kk * 4]; qp[1] = qv[kk * 4 + 1]; qp[2] = qv[kk * 4 + 2]; qp[3] = qv[kk * 4 + 3]; }
@@ -182,7 +183,7 @@ using namespace gq;
 
 extern "C" size_t gptq_b200_colloop_workspace_bytes(int R, int K, int blocksize) {
     (void)K; (void)blocksize;
-    return (size_t)(R > 0 ? R : 0) * BQ_B * sizeof(float);
+    return (size_t)(R > 0 ? R : 0) * BQ_SUPER * BQ_B * sizeof(float);
 }
 
 extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const float* U, int64_t ldu, int blocksize,
@@ -210,9 +211,17 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
         attr_done = true;
     }
     GQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
-    for (int i1 = 0; i1 < K; i1 += blocksize) {
+    // Two-level lazy update (same arithmetic as gptq.py:276, regrouped): after every block only the rest of the current
+    // super-block is brought up to date (narrow GEMM, depth `count`); the columns beyond it receive ONE deep GEMM per
+    // super-block.  Dynamic groups wider than a block read W far ahead (gptq.py:255), so they keep the one-level form.
+    const int sb_blocks = (mode == 1 && groupsize > blocksize) ? 1 : BQ_SUPER;
+    const int64_t lde = (int64_t)BQ_SUPER * BQ_B;
+    int sb_start = 0;
+    for (int i1 = 0, bi = 0; i1 < K; i1 += blocksize, ++bi) {
         const int i2 = (i1 + blocksize < K) ? i1 + blocksize : K;
         const int count = i2 - i1;
+        if (bi % sb_blocks == 0) sb_start = i1;
+        int sb_end = sb_start + sb_blocks * blocksize; if (sb_end > K) sb_end = K;
         if (mode == 1) {
             const int first = ((i1 + groupsize - 1) / groupsize) * groupsize;
             if (first < i2) {
@@ -223,13 +232,18 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
                 if (rc) return rc;
             }
         }
+        float* Eblk = Err + (i1 - sb_start);
         BQArgs a{W, R, K, ldw, U, ldu, i1, count, gidx, scale, zero, ngroups, (float)maxq, maxq < 0 ? 1 : 0,
-                 Q, ldq, codes, ldc, Err, loss};
+                 Q, ldq, codes, ldc, Eblk, lde, loss};
         blockquant_kernel<<<cdiv(R, BQ_ROWS), BQ_THREADS, smem, st>>>(a);
         GQ_LAUNCHED();
-        if (i2 < K) {
-            int rc = sgemm_launch(0, 0, R, K - i2, count, -1.f, Err, BQ_B, U + (int64_t)i1 * ldu + i2, ldu, 1.f,
-                                  W + i2, ldw, SG_FULL, st);
+        if (i2 < sb_end) {            // near: the rest of this super-block
+            int rc = gemm_fp32(0, 0, R, sb_end - i2, count, -1.f, Eblk, lde, U + (int64_t)i1 * ldu + i2, ldu, 1.f,
+                               W + i2, ldw, SG_FULL, st);
+            if (rc) return rc;
+        } else if (i2 < K) {          // far: everything beyond the super-block, one deep GEMM
+            int rc = gemm_fp32(0, 0, R, K - sb_end, sb_end - sb_start, -1.f, Err, lde, U + (int64_t)sb_start * ldu + sb_end,
+                               ldu, 1.f, W + sb_end, ldw, SG_FULL, st);
             if (rc) return rc;
         }
     }

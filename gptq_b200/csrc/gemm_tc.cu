@@ -1,0 +1,343 @@
+// fp32-accurate GEMM on the tensor cores:  C[M,N] <- alpha * op(A) op(B) + beta * C,  fp32 in / out.
+//
+// Used for the trailing updates of the inverse-Cholesky chain (reference gptq.py:177-179) and for the
+// lazy block update W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:] (gptq.py:276).  The reference runs these in
+// fp32 with TF32 disabled (gptq.py:18-19); a single TF32 pass is not accurate enough for code parity
+// (SURVEY Appendix B), so every operand is split on the fly into hi = tf32(x) and lo = x - hi and the
+// product is formed as hi*hi + hi*lo + lo*hi with fp32 accumulation ("3xTF32").
+//
+// One CTA per 128x256 output tile, 320 threads:
+//   warp 0    TMA producer: fp32 operand tiles (BK = 32 = one 128-byte swizzle row) into a 2-stage ring.
+//             Either operand may be K-major (k contiguous: box {32 k, 128 rows}) or MN-major
+//             (m/n contiguous: boxes {32 mn, 32 k}), so all four transpose combinations run natively.
+//   warps 2-9 split the landed stage in place (hi over the raw tile, lo beside it -- same offsets, so the
+//             128B swizzle is preserved), fence.proxy.async, signal the MMA warp; the same warps drain
+//             the TMEM accumulator every CHUNK k-blocks into 128 fp32 registers per thread with
+//             round-to-nearest adds (tcgen05's accumulator truncates: the chain is kept at 12 MMAs),
+//             and finally apply alpha/beta and store C.
+//   warp 1    MMA issuer: per k-block 4 k-steps x 3 x tcgen05.mma.cta_group::1.kind::tf32 (M128 N256 K8)
+//             into one of two 256-column TMEM buffers.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "sgemm.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace gq {
+
+constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 32;
+constexpr int GT_STAGES = 2;
+constexpr int GT_A_BYTES = GT_BM * GT_BK * 4;        // 16 KB
+constexpr int GT_B_BYTES = GT_BN * GT_BK * 4;        // 32 KB
+constexpr int GT_STAGE_BYTES = 2 * (GT_A_BYTES + GT_B_BYTES);   // hi + lo of both operands = 96 KB
+constexpr int GT_THREADS = 320;
+constexpr int GT_CHUNK = 1;                           // k-blocks per TMEM accumulation chain (12 MMAs)
+constexpr int GT_SMEM = GT_STAGES * GT_STAGE_BYTES + 1024 + 256;
+
+struct GemmTcParams {
+    int M, N, Kd; float alpha, beta; float* C; int64_t ldc; int mode; int a_mn, b_mn; uint32_t idesc;
+};
+
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+    const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
+    if ((p.mode & SG_UPPER_TILES) && n0 + GT_BN - 1 < m0) return;      // whole CTA, before any barrier
+    int kbeg = 0, kend = p.Kd;
+    if (p.mode & SG_A_UPPER) kbeg = (m0 / GT_BK) * GT_BK;
+    if (p.mode & SG_B_UPPER) kend = min(p.Kd, n0 + GT_BN);
+    const int nkb = kend > kbeg ? (kend - kbeg + GT_BK - 1) / GT_BK : 0;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GT_STAGES * GT_STAGE_BYTES);   // TMA landed
+    uint64_t* conv_bar = full_bar + GT_STAGES;                                              // split done
+    uint64_t* empty_bar = conv_bar + GT_STAGES;                                             // MMAs retired
+    uint64_t* tfull_bar = empty_bar + GT_STAGES;     // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+        for (int s = 0; s < GT_STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&conv_bar[s], 8); ptx::mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tfull_bar[b], 1); ptx::mbar_init(&tempty_bar[b], 8); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int k0 = kbeg + kb * GT_BK;
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + stage * GT_STAGE_BYTES;
+                uint8_t* sB = sA + 2 * GT_A_BYTES;
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], GT_A_BYTES + GT_B_BYTES);
+                if (p.a_mn) {
+#pragma unroll
+                    for (int q = 0; q < GT_BM / 32; ++q) ptx::tma_load_2d(sA + q * 4096, &tmA, &full_bar[stage], m0 + q * 32, k0);
+                } else {
+                    ptx::tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
+                }
+                if (p.b_mn) {
+#pragma unroll
+                    for (int q = 0; q < GT_BN / 32; ++q) ptx::tma_load_2d(sB + q * 4096, &tmB, &full_bar[stage], n0 + q * 32, k0);
+                } else {
+                    ptx::tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
+                    ptx::tma_load_2d(sB + GT_B_BYTES / 2, &tmB, &full_bar[stage], k0, n0 + 128);
+                }
+                if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            int buf = 0; uint32_t bphase[2] = {0, 0};
+            for (int kb = 0; kb < nkb; ++kb) {
+                const bool chunk_start = (kb % GT_CHUNK) == 0;
+                if (chunk_start) {
+                    ptx::mbar_wait(&tempty_bar[buf], bphase[buf] ^ 1);
+                    ptx::tc_fence_after();
+                }
+                ptx::mbar_wait(&conv_bar[stage], phase);
+                ptx::tc_fence_after();
+                const uint32_t sA = ptx::smem_u32(smem + stage * GT_STAGE_BYTES);
+                const uint32_t sB = sA + 2 * GT_A_BYTES;
+                const uint32_t d_tmem = tmem_base + buf * GT_BN;
+#pragma unroll
+                for (int ks = 0; ks < GT_BK / 8; ++ks) {
+                    // K-major: +32 B per k-step inside the 128 B swizzle row; MN-major: +1024 B (8 k-rows)
+                    const uint32_t aoff = p.a_mn ? ks * 1024 : ks * 32;
+                    const uint32_t boff = p.b_mn ? ks * 1024 : ks * 32;
+                    // K-major: SWIZZLE_128B, 8-row atoms (SBO 1024).  MN-major tf32: SWIZZLE_128B_BASE32B, 32-element x
+                    // 4-k-row atoms: LBO = panel stride (next 32 m/n), SBO = 512 (next 4 k-rows).
+                    const uint32_t albo = p.a_mn ? 4096 : 16, blbo = p.b_mn ? 4096 : 16;
+                    const uint32_t asbo = p.a_mn ? 512 : 1024, bsbo = p.b_mn ? 512 : 1024;
+                    const uint32_t alt = p.a_mn ? 1 : 2, blt = p.b_mn ? 1 : 2;
+                    const uint64_t ahi = ptx::make_smem_desc(sA + aoff, albo, asbo, alt);
+                    const uint64_t alo = ptx::make_smem_desc(sA + GT_A_BYTES + aoff, albo, asbo, alt);
+                    const uint64_t bhi = ptx::make_smem_desc(sB + boff, blbo, bsbo, blt);
+                    const uint64_t blo = ptx::make_smem_desc(sB + GT_B_BYTES + boff, blbo, bsbo, blt);
+                    const uint32_t acc0 = (chunk_start && ks == 0) ? 0u : 1u;
+                    ptx::mma_tf32_ss(d_tmem, alo, bhi, p.idesc, acc0);        // small terms first
+                    ptx::mma_tf32_ss(d_tmem, ahi, blo, p.idesc, 1u);
+                    ptx::mma_tf32_ss(d_tmem, ahi, bhi, p.idesc, 1u);
+                }
+                ptx::tc_commit(&empty_bar[stage]);
+                if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
+                if ((kb % GT_CHUNK) == GT_CHUNK - 1 || kb == nkb - 1) {
+                    ptx::tc_commit(&tfull_bar[buf]);
+                    bphase[buf] ^= 1;
+                    buf ^= 1;
+                }
+            }
+        }
+    } else {
+        // ===================================================== converter + drain + epilogue warps
+        const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+        const int ct = threadIdx.x - 64;                       // 0..255
+        float acc[128];
+#pragma unroll
+        for (int q = 0; q < 128; ++q) acc[q] = 0.f;
+        int stage = 0; uint32_t phase = 0;
+        int dbuf = 0; uint32_t dphase[2] = {0, 0};
+        auto drain = [&]() {
+            ptx::mbar_wait(&tfull_bar[dbuf], dphase[dbuf]);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + dbuf * GT_BN + half * 128 + ((uint32_t)(quad * 32) << 16);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                float v[32];
+                ptx::tmem_ld_32x32(taddr + cb * 32, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int q = 0; q < 32; ++q) acc[cb * 32 + q] = __fadd_rn(acc[cb * 32 + q], v[q]);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty_bar[dbuf]);
+            dphase[dbuf] ^= 1;
+            dbuf ^= 1;
+        };
+        for (int kb = 0; kb < nkb; ++kb) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            uint8_t* base = smem + stage * GT_STAGE_BYTES;
+            // A: raw/hi at [0, A), lo at [A, 2A);  B: raw/hi at [2A, 2A+B), lo at [2A+B, 2A+2B)
+#pragma unroll
+            for (int it = 0; it < (GT_A_BYTES + GT_B_BYTES) / 16 / 256; ++it) {
+                const int idx = ct + it * 256;                                  // float4 index over A then B
+                const bool isA = idx < GT_A_BYTES / 16;
+                uint8_t* hi = isA ? base + idx * 16 : base + 2 * GT_A_BYTES + (idx - GT_A_BYTES / 16) * 16;
+                uint8_t* lo = hi + (isA ? GT_A_BYTES : GT_B_BYTES);
+                float4 v = *reinterpret_cast<const float4*>(hi);
+                float4 h, l;                    // hi = rn_tf32(x); lo = rn_tf32(x - hi)  (x - hi is exact)
+                h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
+                h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
+                h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
+                h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
+                *reinterpret_cast<float4*>(hi) = h;
+                *reinterpret_cast<float4*>(lo) = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&conv_bar[stage]);
+            if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
+            // drain the previous chunk once the first k-block of this chunk has been handed to the MMA warp
+            if (kb >= GT_CHUNK && (kb % GT_CHUNK) == 0) drain();
+        }
+        if (nkb > 0) drain();                                                   // last chunk
+
+        const int row = m0 + quad * 32 + lane;
+        const int col0 = n0 + half * 128;
+        if (row < p.M) {
+            float* dst = p.C + (int64_t)row * p.ldc + col0;
+            const int cols_ok = min(128, p.N - col0);
+            const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
+#pragma unroll
+            for (int cb = 0; cb < 4; ++cb) {
+                float* o = dst + cb * 32;
+                const int nc = cols_ok - cb * 32;
+                if (nc >= 32 && vec) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float4 r;
+                        if (p.beta != 0.f) {
+                            const float4 c = *reinterpret_cast<const float4*>(o + q * 4);
+                            r.x = fmaf(p.alpha, acc[cb * 32 + q * 4 + 0], p.beta * c.x); r.y = fmaf(p.alpha, acc[cb * 32 + q * 4 + 1], p.beta * c.y);
+                            r.z = fmaf(p.alpha, acc[cb * 32 + q * 4 + 2], p.beta * c.z); r.w = fmaf(p.alpha, acc[cb * 32 + q * 4 + 3], p.beta * c.w);
+                        } else {
+                            r.x = p.alpha * acc[cb * 32 + q * 4 + 0]; r.y = p.alpha * acc[cb * 32 + q * 4 + 1];
+                            r.z = p.alpha * acc[cb * 32 + q * 4 + 2]; r.w = p.alpha * acc[cb * 32 + q * 4 + 3];
+                        }
+                        *reinterpret_cast<float4*>(o + q * 4) = r;
+                    }
+                } else if (nc > 0) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (q < nc) o[q] = (p.beta != 0.f) ? fmaf(p.alpha, acc[cb * 32 + q], p.beta * o[q]) : p.alpha * acc[cb * 32 + q];
+                }
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn2 get_encode_fn2() {
+    static EncodeTiledFn2 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn2>(p);
+    }
+    return fn;
+}
+
+// Operand with logical shape [mn_extent x k_extent].  mn_major: stored [k][mn] (mn contiguous), else [mn][k].
+static int make_operand_map(CUtensorMap* tm, const float* ptr, int64_t ld, int mn_extent, int k_extent, bool mn_major) {
+    EncodeTiledFn2 enc = get_encode_fn2();
+    if (!enc) return set_err(999, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2], gstr[1];
+    cuuint32_t box[2], estr[2] = {1, 1};
+    if (mn_major) { gdim[0] = (cuuint64_t)mn_extent; gdim[1] = (cuuint64_t)k_extent; box[0] = 32; box[1] = GT_BK; }
+    else          { gdim[0] = (cuuint64_t)k_extent; gdim[1] = (cuuint64_t)mn_extent; box[0] = GT_BK; box[1] = 128; }
+    gstr[0] = (cuuint64_t)ld * 4;
+    CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return set_err(1000 + (int)cr, "cuTensorMapEncodeTiled(fp32) failed (%d)", (int)cr);
+    return 0;
+}
+
+bool gemm_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc) {
+    return (lda % 4 == 0) && (ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0) &&
+           ((reinterpret_cast<uintptr_t>(B) & 15) == 0) && C != nullptr && ldc > 0;
+}
+
+int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda, const float* B,
+                   int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return 0;
+    CUtensorMap tmA, tmB;
+    int rc = make_operand_map(&tmA, A, lda, M, Kd, transa != 0);
+    if (rc) return rc;
+    rc = make_operand_map(&tmB, B, ldb, N, Kd, transb == 0);
+    if (rc) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+        attr_done = true;
+    }
+    GemmTcParams p;
+    p.M = M; p.N = N; p.Kd = Kd; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.mode = mode;
+    p.a_mn = transa ? 1 : 0; p.b_mn = transb ? 0 : 1;
+    p.idesc = ptx::make_idesc(2, p.a_mn, p.b_mn, GT_BM, GT_BN);
+    dim3 grid(cdiv(N, GT_BN), cdiv(M, GT_BM));
+    gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, st>>>(tmA, tmB, p);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+static int backend_from_env() {
+    const char* e = getenv("GPTQ_B200_GEMM_BACKEND");
+    if (e && (e[0] == 's' || e[0] == '0')) return 0;       // "simt"
+    return 1;
+}
+int g_gemm_backend = backend_from_env();
+
+int gemm_fp32(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda, const float* B,
+              int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st) {
+    if (g_gemm_backend == 1 && gemm_tc_supported(A, lda, B, ldb, C, ldc))
+        return gemm_tc_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, mode, st);
+    return sgemm_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, mode, st);
+}
+
+}  // namespace gq
+
+using namespace gq;
+
+extern "C" int gptq_b200_set_gemm_backend(int backend) {
+    GQ_ARG(backend == 0 || backend == 1, 1, "0 = CUDA cores, 1 = tensor cores (3xTF32)");
+    int old = g_gemm_backend;
+    g_gemm_backend = backend;
+    return old < 0 ? 0 : 0;
+}
+
+extern "C" int gptq_b200_gemm3x(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda,
+                                const float* B, int64_t ldb, float beta, float* C, int64_t ldc, void* stream) {
+    GQ_ARG(M >= 0, 3, "M<0"); GQ_ARG(N >= 0, 4, "N<0"); GQ_ARG(Kd >= 0, 5, "K<0");
+    GQ_ARG(A, 7, "null"); GQ_ARG(B, 9, "null"); GQ_ARG(C, 12, "null");
+    GQ_ARG(lda >= (transa ? M : Kd) && lda % 4 == 0, 8, "lda too small or not a multiple of 4");
+    GQ_ARG(ldb >= (transb ? Kd : N) && ldb % 4 == 0, 10, "ldb too small or not a multiple of 4");
+    GQ_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, 7, "A/B must be 16-byte aligned");
+    GQ_ARG(ldc >= N, 13, "ldc<N");
+    return gemm_tc_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, SG_FULL, as_stream(stream));
+}

@@ -114,6 +114,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
     d |= (uint64_t)2 << 61;           // layout type SWIZZLE_128B
     return d;
 }
+// Same with an explicit layout type: 2 = SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks,
+// 4-row atoms -- the only layout tcgen05 accepts for MN-major tf32 operands; TMA: SWIZZLE_128B_ATOM_32B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
 // Instruction descriptor for kind::f16 / kind::tf32, dense, fp32 accumulate.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32;  *_mn: 1 = MN-major operand, 0 = K-major.
 __host__ __device__ constexpr uint32_t make_idesc(int fmt, int a_mn, int b_mn, int M, int N) {

@@ -16,3 +16,14 @@ int sgemm_launch(int transa, int transb, int M, int N, int Kd, float alpha, cons
                  const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st);
 
 }  // namespace gq
+
+namespace gq {
+// Tensor-core (3xTF32) variant with the same contract (gemm_tc.cu); needs lda/ldb % 4 == 0 and 16-byte aligned A, B.
+bool gemm_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc);
+int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda,
+                   const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st);
+// Backend selection used by the chain and the lazy update: 1 = tensor cores when supported (default), 0 = CUDA cores.
+extern int g_gemm_backend;
+int gemm_fp32(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda,
+              const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st);
+}  // namespace gq

@@ -173,6 +173,15 @@ int gptq_b200_unpack_codes(const int32_t* qweight, int R, int K, int bits,
 int gptq_b200_sgemm(int transa, int transb, int M, int N, int Kd, float alpha,
                     const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                     float* C, int64_t ldc, void* stream);
+/* Same contract on the tensor cores: tcgen05 kind::tf32, operands split hi/lo on the fly,
+ * hi*hi + hi*lo + lo*hi ("3xTF32"), fp32 accumulation drained to registers every 128 k.
+ * Requires lda, ldb multiples of 4 and 16-byte aligned A, B. */
+int gptq_b200_gemm3x(int transa, int transb, int M, int N, int Kd, float alpha,
+                     const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
+                     float* C, int64_t ldc, void* stream);
+/* Which of the two the chain and the lazy update use: 1 = tensor cores (default), 0 = CUDA cores
+ * (also selectable with GPTQ_B200_GEMM_BACKEND=simt).  Process-wide; for tests and A/B timing. */
+int gptq_b200_set_gemm_backend(int backend);
 
 #ifdef __cplusplus
 }

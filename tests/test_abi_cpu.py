@@ -51,7 +51,7 @@ def test_abi_version_and_error_string(lib):
     rc = L.gptq_b200_hinv_upper(1, 100, 100, 2, 100, 1, 1, 0, 0)
     assert rc == -2
     assert L.gptq_b200_hinv_upper_workspace_bytes(256) == 128 * 128 * 4
-    assert L.gptq_b200_colloop_workspace_bytes(1000, 4096, 128) == 1000 * 128 * 4
+    assert L.gptq_b200_colloop_workspace_bytes(1000, 4096, 128) == 1000 * 512 * 4
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

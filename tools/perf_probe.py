@@ -115,11 +115,11 @@ def probe_pack(R, K, bits):
 
 def probe_sgemm(M, N, Kd):
     A = torch.randn(M, Kd, device=DEV); B = torch.randn(Kd, N, device=DEV); C = torch.zeros(M, N, device=DEV)
-
-    def run():
-        _lib.check(lib.gptq_b200_sgemm(0, 0, M, N, Kd, 1.0, A.data_ptr(), Kd, B.data_ptr(), N, 0.0, C.data_ptr(), N, _lib.stream()), "sgemm")
-    best, _ = timeit(run)
-    print(json.dumps(dict(op="sgemm", M=M, N=N, K=Kd, ms=best, tflops=2.0 * M * N * Kd / best / 1e9)))
+    for name, fn in (("sgemm", lib.gptq_b200_sgemm), ("gemm3x", lib.gptq_b200_gemm3x)):
+        def run():
+            _lib.check(fn(0, 0, M, N, Kd, 1.0, A.data_ptr(), Kd, B.data_ptr(), N, 0.0, C.data_ptr(), N, _lib.stream()), name)
+        best, _ = timeit(run)
+        print(json.dumps(dict(op=name, M=M, N=N, K=Kd, ms=best, tflops=2.0 * M * N * Kd / best / 1e9)))
 
 
 if __name__ == "__main__":
@@ -127,11 +127,13 @@ if __name__ == "__main__":
     if "syrk" in what:
         for K, T in ((4096, 32768), (4096, 2048), (11008, 32768), (768, 32768), (2048, 32768)):
             probe_syrk(K, T)
-        for chunk in (256, 1024, 4096):
+        for chunk in (64, 128, 256, 1024, 4096):
             probe_syrk(4096, 32768, chunk)
     if "sgemm" in what:
         probe_sgemm(4096, 4096, 4096)
         probe_sgemm(4096, 4096, 128)
+        probe_sgemm(128, 128, 128)
+        probe_sgemm(512, 512, 512)
     if "hinv" in what:
         for K in (1024, 4096):
             probe_hinv(K)
