@@ -197,6 +197,15 @@ def make_inputs(dev, rank, world, host=False):
     return acts, ws
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(dev):
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[dev]
+
+
 def quantize_layer(dev, acts, weights, world, from_host):
     """One step: the reference driver's per-layer flow (llama.py:97-170) over our GPTQ / Quantizer / pack."""
     import torch.nn as nn
@@ -218,11 +227,36 @@ def quantize_layer(dev, acts, weights, world, from_host):
             g.quantizer.configure(WBITS, perchannel=True, sym=False, mse=False)
             gs.append(g)
         X = acts[LINEARS[subset[0]][3]]
-        for j in range(X.shape[0]):
-            xj = X[j].to(dev, non_blocking=True) if from_host else X[j]
-            xj = xj.unsqueeze(0)
-            for g in gs:                                  # the forward hooks of q/k/v see the same tensor
-                g.add_batch(xj, None)
+        if from_host:
+            # the caller's side of the public API: samples arrive from pinned host memory; a copy stream
+            # prefetches sample j+1 into a second device buffer while sample j is being staged
+            cs = _copy_stream(dev)
+            cur = torch.cuda.current_stream()
+            bufs = [torch.empty(X.shape[1:], dtype=X.dtype, device=dev) for _ in range(2)]
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            freed = [torch.cuda.Event(), torch.cuda.Event()]
+            with torch.cuda.stream(cs):
+                bufs[0].copy_(X[0], non_blocking=True)
+                ready[0].record(cs)
+            for j in range(X.shape[0]):
+                b = j & 1
+                if j + 1 < X.shape[0]:
+                    nb = (j + 1) & 1
+                    with torch.cuda.stream(cs):
+                        if j >= 1:
+                            cs.wait_event(freed[nb])
+                        bufs[nb].copy_(X[j + 1], non_blocking=True)
+                        ready[nb].record(cs)
+                cur.wait_event(ready[b])
+                xj = bufs[b].unsqueeze(0)
+                for g in gs:
+                    g.add_batch(xj, None)
+                freed[b].record(cur)
+        else:
+            for j in range(X.shape[0]):
+                xj = X[j].unsqueeze(0)
+                for g in gs:                              # the forward hooks of q/k/v see the same tensor
+                    g.add_batch(xj, None)
         for g in gs:
             if world > 1:
                 gd.allreduce_hessian(g)

@@ -41,6 +41,7 @@ SIGNATURES = {
     "gptq_b200_colloop_workspace_bytes": (_sz, [_i, _i, _i]),
     "gptq_b200_colloop": (_i, [_vp, _i, _i, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _f,
                                _vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "gptq_b200_selftest_div": (_i, [C.c_uint64, C.c_uint32, _i, _vp, _vp]),
     "gptq_b200_finalize": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _i, _i64, _vp, _i64, _vp]),
     "gptq_b200_pack_codes": (_i, [_vp, _i, _i, _i64, _i, _vp, _vp]),
     "gptq_b200_pack_weights": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp]),

@@ -17,19 +17,20 @@
 namespace gq {
 
 constexpr int CB = 128;            // block size
-constexpr int CP = CB + 1;         // smem pitch (conflict-free row-per-thread access)
 
 // A_jj (upper triangle read) -> Dinv = R_jj^-1 (dense 128x128, strict lower zero), A_jj = R_jj R_jj^T.
 //
-// 256 threads as a 16x16 grid; thread (ty,tx) owns the 8x8 cyclic sub-matrix
+// 256 threads as a 16x16 grid, tid = tx*16 + ty; thread (ty,tx) owns the 8x8 cyclic sub-matrix
 //     rows a*16+ty, cols b*16+tx  (a,b = 0..7)
 // of the 128x128 block IN REGISTERS, so each of the 128 sequential steps is one rank-1 update of a
-// register tile: the pivot column (and, for the inverse, the pivot row) is broadcast through a
-// 128-float shared-memory vector, two block barriers per step.  The step loop is written as
-// (outer block index, statically unrolled) x (inner 16, rolled) so every register index is static
-// and tiles that lie outside the still-active triangle are skipped at compile time.
+// register tile.  The 16 owners of a matrix column are one half-warp, so the pivot reaches them by
+// shuffle and a step needs ONE block barrier (the broadcast column is double-buffered in smem).
+// The step loop is (outer block index, statically unrolled) x (inner 16, rolled): every register
+// index is static and tiles outside the still-active triangle are skipped at compile time.
 //   phase 1: right-looking backward Cholesky  A = R R^T  (columns 127 .. 0)
-//   phase 2: X = R^-1 by forward column elimination of  X R = I  (columns 0 .. 127)
+//   phase 2: X = R^-1 by forward column elimination of  X R = I  (columns 0 .. 127), R read from smem
+constexpr int CT = CB + 1;         // smem pitch
+
 // 1/sqrt(v): MUFU.RSQ + one Newton step (error < 1 ulp; nothing downstream is bit-matched to LAPACK)
 __device__ __forceinline__ float inv_sqrt(float v) {
     float y = rsqrtf(v);
@@ -37,20 +38,28 @@ __device__ __forceinline__ float inv_sqrt(float v) {
 }
 
 template <int JB>
-__device__ __forceinline__ void chol_phase1_block(float (&r)[8][8], float* colb, float* rd, int32_t* info, int base_index,
+__device__ __forceinline__ void chol_phase1_block(float (&r)[8][8], float* colb2, float* rd, int32_t* info, int base_index,
                                                   int tx, int ty) {
 #pragma unroll 1
     for (int jt = 15; jt >= 0; --jt) {
         const int j = JB * 16 + jt;
-        const float rinv = rd[j];                        // 1 / R[j][j], published by the pivot owner
-        if (tx == jt) {                                  // owners of column j: rows a*16+ty, a <= JB
+        float* colb = colb2 + (jt & 1) * CB;
+        if ((int)(threadIdx.x >> 5) == (jt >> 1)) {          // the warp holding column j (warp-uniform)
+            const float v = __shfl_sync(0xffffffffu, r[JB][JB], ((jt & 1) << 4) | jt);     // pivot (j,j)
+            const float rinv = inv_sqrt(v);
+            if (tx == jt) {
+                if (ty == jt) {
+                    if (!(v > 0.f)) atomicCAS(info, 0, base_index + j + 1);
+                    rd[j] = rinv;
+                }
 #pragma unroll
-            for (int a = 0; a <= JB; ++a) {
-                const int row = a * 16 + ty;
-                float c = r[a][JB] * rinv;               // row == j: v * rsqrt(v) = sqrt(v)
-                if (row > j) c = 0.f;
-                r[a][JB] = c;
-                colb[row] = c;
+                for (int a = 0; a <= JB; ++a) {
+                    const int row = a * 16 + ty;
+                    float c = r[a][JB] * rinv;                 // row == j: v * rsqrt(v) = sqrt(v)
+                    if (row > j) c = 0.f;
+                    r[a][JB] = c;
+                    colb[row] = c;
+                }
             }
         }
         __syncthreads();
@@ -66,34 +75,17 @@ __device__ __forceinline__ void chol_phase1_block(float (&r)[8][8], float* colb,
                 const bool act = (a < JB || ty < jt) && (b < JB || tx < jt);     // row < j && col < j
                 if (act) r[a][b] = fmaf(-cr[a], cc[b], r[a][b]);
             }
-        // next pivot: element (j-1, j-1) is final now
-        if (j > 0) {
-            const int pj = j - 1;
-            if (tx == (pj & 15) && ty == (pj & 15)) {
-                const float v = (jt > 0) ? r[JB][JB] : r[JB > 0 ? JB - 1 : 0][JB > 0 ? JB - 1 : 0];
-                if (!(v > 0.f)) atomicCAS(info, 0, base_index + pj + 1);
-                rd[pj] = inv_sqrt(v);
-            }
-        }
-        __syncthreads();
     }
 }
 
 template <int CBI>
-__device__ __forceinline__ void chol_phase2_block(const float (&r)[8][8], float (&x)[8][8], float* colb2, float* rowb2,
-                                                  const float* rd, int tx, int ty) {
+__device__ __forceinline__ void chol_phase2_block(float (&x)[8][8], float* colb2, const float* S, const float* rd, int tx, int ty) {
 #pragma unroll 1
     for (int ct = 0; ct < 16; ++ct) {
         const int c = CBI * 16 + ct;
-        float* rowb = rowb2 + (ct & 1) * CB;             // double-buffered: no trailing barrier needed
         float* colb = colb2 + (ct & 1) * CB;
-        if (ty == ct) {                                  // owners of row c of R: cols b*16+tx, b >= CBI
-#pragma unroll
-            for (int b = CBI; b < 8; ++b) rowb[b * 16 + tx] = r[CBI][b];
-        }
-        __syncthreads();
-        const float dinv = rd[c];                        // 1 / R[c][c] from phase 1
         if (tx == ct) {                                  // owners of column c of X: rows a*16+ty, a <= CBI
+            const float dinv = rd[c];                    // 1 / R[c][c] from phase 1
 #pragma unroll
             for (int a = 0; a <= CBI; ++a) {
                 const float v = x[a][CBI] * dinv;
@@ -106,7 +98,7 @@ __device__ __forceinline__ void chol_phase2_block(const float (&r)[8][8], float 
 #pragma unroll
         for (int a = 0; a <= CBI; ++a) xc[a] = colb[a * 16 + ty];
 #pragma unroll
-        for (int b = CBI; b < 8; ++b) rr[b] = rowb[b * 16 + tx];
+        for (int b = CBI; b < 8; ++b) rr[b] = S[c * CT + b * 16 + tx];          // row c of R
 #pragma unroll
         for (int a = 0; a <= CBI; ++a)
 #pragma unroll
@@ -120,12 +112,13 @@ __device__ __forceinline__ void chol_phase2_block(const float (&r)[8][8], float 
 __global__ void __launch_bounds__(256, 1)
 chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict__ Dinv, int64_t ldd,
                  int32_t* __restrict__ info, int base_index) {
+    extern __shared__ float S[];                         // [128][129]: R for phase 2
     __shared__ float colb[2 * CB];
-    __shared__ float rowb[2 * CB];
     __shared__ float rd[CB];                             // 1 / R[j][j]
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tid = threadIdx.x;
+    const int tx = tid >> 4, ty = tid & 15;
 
-    float r[8][8];
+    float r[8][8];                                       // 64 independent loads per thread: one memory latency
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -133,14 +126,7 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
             const int row = a * 16 + ty, col = b * 16 + tx;
             r[a][b] = (col >= row) ? Ablk[(int64_t)row * lda + col] : 0.f;
         }
-    if (tx == 15 && ty == 15) {
-        const float v = r[7][7];
-        if (!(v > 0.f)) atomicCAS(info, 0, base_index + CB);
-        rd[CB - 1] = inv_sqrt(v);
-    }
-    __syncthreads();
 
-    // ---------------- phase 1: for j = 127..0: scale column j, rank-1 update of the leading j x j block
     chol_phase1_block<7>(r, colb, rd, info, base_index, tx, ty);
     chol_phase1_block<6>(r, colb, rd, info, base_index, tx, ty);
     chol_phase1_block<5>(r, colb, rd, info, base_index, tx, ty);
@@ -150,20 +136,25 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
     chol_phase1_block<1>(r, colb, rd, info, base_index, tx, ty);
     chol_phase1_block<0>(r, colb, rd, info, base_index, tx, ty);
 
-    // ---------------- phase 2: x = I; for c = 0..127: x[:,c] /= R[c][c]; x[:,c'] -= x[:,c] R[c][c'] (c' > c)
+    __syncthreads();                                     // all phase-1 reads of colb done; S free
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) S[(a * 16 + ty) * CT + b * 16 + tx] = r[a][b];       // publish R (lower = 0)
     float x[8][8];
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
         for (int b = 0; b < 8; ++b) x[a][b] = (a == b && tx == ty) ? 1.f : 0.f;
-    chol_phase2_block<0>(r, x, colb, rowb, rd, tx, ty);
-    chol_phase2_block<1>(r, x, colb, rowb, rd, tx, ty);
-    chol_phase2_block<2>(r, x, colb, rowb, rd, tx, ty);
-    chol_phase2_block<3>(r, x, colb, rowb, rd, tx, ty);
-    chol_phase2_block<4>(r, x, colb, rowb, rd, tx, ty);
-    chol_phase2_block<5>(r, x, colb, rowb, rd, tx, ty);
-    chol_phase2_block<6>(r, x, colb, rowb, rd, tx, ty);
-    chol_phase2_block<7>(r, x, colb, rowb, rd, tx, ty);
+    __syncthreads();
+    chol_phase2_block<0>(x, colb, S, rd, tx, ty);
+    chol_phase2_block<1>(x, colb, S, rd, tx, ty);
+    chol_phase2_block<2>(x, colb, S, rd, tx, ty);
+    chol_phase2_block<3>(x, colb, S, rd, tx, ty);
+    chol_phase2_block<4>(x, colb, S, rd, tx, ty);
+    chol_phase2_block<5>(x, colb, S, rd, tx, ty);
+    chol_phase2_block<6>(x, colb, S, rd, tx, ty);
+    chol_phase2_block<7>(x, colb, S, rd, tx, ty);
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
@@ -192,7 +183,7 @@ static void hinv_rec(HinvCtx& c, int a, int b) {
     if (c.rc) return;
     if (b - a == 1) {
         const int c0 = a * CB;
-        chol_diag_kernel<<<1, 256, 0, c.st>>>(c.A + (int64_t)c0 * c.lda + c0, c.lda, c.V + (int64_t)c0 * c.ldv + c0,
+        chol_diag_kernel<<<1, 256, c.smem, c.st>>>(c.A + (int64_t)c0 * c.lda + c0, c.lda, c.V + (int64_t)c0 * c.ldv + c0,
                                                    c.ldv, c.info, c0);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return;
@@ -244,7 +235,12 @@ extern "C" int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, float* U, int
     GQ_ARG(info, 6, "null"); GQ_ARG(ws, 7, "null");
     GQ_ARG(ws_bytes >= gptq_b200_hinv_upper_workspace_bytes(Kp), 8, "workspace too small");
     cudaStream_t st = as_stream(stream);
-    const size_t smem = 0;
+    const size_t smem = (size_t)CB * CT * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GQ_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
     GQ_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     GQ_CUDA(cudaMemset2DAsync(U, ldu * sizeof(float), 0, (size_t)Kp * sizeof(float), Kp, st));
     HinvCtx c{A, lda, U, ldu, static_cast<float*>(ws), info, st, smem, 0};

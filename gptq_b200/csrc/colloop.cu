@@ -1,87 +1,118 @@
 // (3) The fasterquant column loop (reference gptq.py:191-276, standard branch).
 //
 // Per block of <=128 columns:
-//   blockquant_kernel -- rows are independent, so a CTA owns 16 rows; 8 lanes share a row and
-//     keep its 128-column W1 slice in registers (16 per lane, 4 chunks of 4 consecutive columns),
-//     Hinv1 (128x128) and the per-(row,column) scale/zero live in shared memory.  For every column
-//     the owner lane broadcasts w with a shuffle, all 8 lanes quantize it (quant.py:6-10, same
-//     operation order and IEEE roundings as torch), form err = (w-q)/d and apply the rank-1 update
-//     to the columns they own -- product and subtraction rounded separately, exactly like
+//   blockquant_kernel -- rows are independent, so a CTA owns a slab of rows (one CTA per SM; the slab is
+//     sized so that ceil(R / slab) <= #SMs where possible).  Four lanes share a row and keep its
+//     128-column W1 slice in registers (32 per lane: 8 chunks of 4 consecutive columns); Hinv1 (128x128)
+//     and the per-(row,column) scale / zero / 1/scale live in shared memory.  For every column the owner
+//     lane broadcasts w with a shuffle, the four lanes quantize it (quant.py:6-10, same operation order
+//     and roundings as torch), form err = (w-q)/d and apply the rank-1 update to the columns they own --
+//     product and subtraction rounded separately, exactly like
 //     W1[:, i:] -= err1.unsqueeze(1).matmul(Hinv1[i, i:].unsqueeze(0)) (gptq.py:270).
-//     Finished columns' registers are recycled to hold err so Q / codes / Err1 leave with
-//     16-byte coalesced stores at the end of the block.
-//   lazy update -- W[:, i2:] -= Err1 @ U[i1:i2, i2:] (gptq.py:276) as an fp32 GEMM.
+//     Finished columns' registers are recycled to hold err, so Q / codes / Err1 leave with 16-byte
+//     stores at the end of the block.
+//     The two IEEE divisions of the per-column dependency chain (w/scale, (w-q)/d) use reciprocals that
+//     are hoisted out of the chain (1/scale per (row,column) at block start, 1/d per column) and the
+//     exactly-rounded quotient is recovered with FMAs: q0 = a*y; r = a - q0*b; q1 = q0 + r*y, applied
+//     twice (the second pass is the identity on a correctly rounded quotient).  gptq_b200_selftest_div
+//     checks bit-equality with div.rn.f32 on the GPU (tests/test_gpu_parity.py).
+//   lazy update -- W[:, i2:] -= Err1 @ U[i1:i2, i2:] (gptq.py:276) as an fp32-accurate GEMM, two-level.
 // Dynamic groups (gptq.py:253-255) are fitted by find_params on the CURRENT global W when the
 // block containing the group start begins, which is what the reference's stale read amounts to.
 //
-// Compiled with --fmad=false: nothing in this file may be contracted into an FMA.
+// Compiled with --fmad=false: no a*b+c in this file is contracted; every FMA below is an explicit fmaf.
 #include "sgemm.cuh"
 
 namespace gq {
 
-constexpr int BQ_ROWS = 16;
-constexpr int BQ_THREADS = 128;
 constexpr int BQ_B = 128;            // max block width handled by the kernel
-constexpr int BQ_SP = BQ_B + 1;      // pitch of the scale/zero tiles
+constexpr int BQ_SP = BQ_B + 1;      // pitch of the per-(row,column) tiles
 constexpr int BQ_SUPER = 4;          // blocks per super-block of the two-level lazy update
+constexpr int BQ_MAX_ROWS = 96;      // rows per CTA: 64 KB + 3 * rows * 516 B of shared memory <= 227 KB
 
 struct BQArgs {
     float* W; int R; int K; int64_t ldw; const float* U; int64_t ldu; int i1; int count;
     const int32_t* gidx; const float* scale; const float* zero; int ng; float maxq; int trits;
-    float* Q; int64_t ldq; uint8_t* codes; int64_t ldc; float* Err; int64_t lde; double* loss;
+    float* Q; int64_t ldq; uint8_t* codes; int64_t ldc; float* Err; int64_t lde; double* loss; int rows_per_cta;
 };
 
-__global__ void __launch_bounds__(BQ_THREADS)
+// Exactly rounded a / b given y = RN(1 / b): two residual-correction passes.
+__device__ __forceinline__ float div_by_recip(float a, float b, float y) {
+    float q = __fmul_rn(a, y);
+    float r = fmaf(-q, b, a);
+    q = fmaf(r, y, q);
+    r = fmaf(-q, b, a);
+    q = fmaf(r, y, q);
+    return q;
+}
+
+__global__ void __launch_bounds__(BQ_MAX_ROWS * 4, 1)
 blockquant_kernel(BQArgs a) {
     extern __shared__ __align__(16) float sm[];
+    const int RPC = a.rows_per_cta;
     float* Hs = sm;                          // [128][128]
-    float* Ss = Hs + BQ_B * BQ_B;            // [16][129]
-    float* Zs = Ss + BQ_ROWS * BQ_SP;        // [16][129]
-    __shared__ double s_loss[BQ_THREADS / 32];
+    float* Ss = Hs + BQ_B * BQ_B;            // [RPC][129]  scale
+    float* Zs = Ss + RPC * BQ_SP;            // [RPC][129]  zero
+    float* Ys = Zs + RPC * BQ_SP;            // [RPC][129]  RN(1/scale)
+    __shared__ float s_rd[BQ_B];             // RN(1 / Hinv1[i][i])
+    __shared__ double s_loss[BQ_MAX_ROWS * 4 / 32];
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int l8 = lane & 7, rl = warp * 4 + (lane >> 3);
-    const int row = blockIdx.x * BQ_ROWS + rl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+    const int l4 = lane & 3, rl = tid >> 2;
+    const int row = blockIdx.x * RPC + rl;
     const bool rvalid = row < a.R;
     const int count = a.count, i1 = a.i1;
 
-    // ---- stage Hinv1 = U[i1:i1+count, i1:i1+count] (zero padded)
+    // ---- stage Hinv1 = U[i1:i1+count, i1:i1+count] (zero padded); independent loads, unrolled for memory-level parallelism
     const bool uvec = ((a.ldu & 3) == 0) && ((i1 & 3) == 0) && ((((uintptr_t)a.U) & 15) == 0);
-    for (int idx = tid; idx < BQ_B * (BQ_B / 4); idx += BQ_THREADS) {
-        int r = idx >> 5, c4 = (idx & 31) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < count) {
-            const float* p = a.U + (int64_t)(i1 + r) * a.ldu + i1 + c4;
-            if (uvec && c4 + 3 < count) v = *reinterpret_cast<const float4*>(p);
-            else {
+    if (uvec && count == BQ_B) {
+#pragma unroll 8
+        for (int idx = tid; idx < BQ_B * (BQ_B / 4); idx += nthreads) {
+            const int r = idx >> 5, c4 = (idx & 31) * 4;
+            *reinterpret_cast<float4*>(&Hs[r * BQ_B + c4]) =
+                *reinterpret_cast<const float4*>(a.U + (int64_t)(i1 + r) * a.ldu + i1 + c4);
+        }
+    } else {
+        for (int idx = tid; idx < BQ_B * (BQ_B / 4); idx += nthreads) {
+            int r = idx >> 5, c4 = (idx & 31) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < count) {
+                const float* p = a.U + (int64_t)(i1 + r) * a.ldu + i1 + c4;
                 if (c4 + 0 < count) v.x = p[0];
                 if (c4 + 1 < count) v.y = p[1];
                 if (c4 + 2 < count) v.z = p[2];
                 if (c4 + 3 < count) v.w = p[3];
             }
+            *reinterpret_cast<float4*>(&Hs[r * BQ_B + c4]) = v;
         }
-        *reinterpret_cast<float4*>(&Hs[r * BQ_B + c4]) = v;
     }
-    // ---- stage the quantizer of every (row, column) of the block
-    for (int idx = tid; idx < BQ_ROWS * BQ_B; idx += BQ_THREADS) {
-        int r = idx >> 7, c = idx & 127;
-        int gr = blockIdx.x * BQ_ROWS + r;
-        float s = 1.f, z = 0.f;
-        if (gr < a.R && c < count) {
-            int g = a.gidx ? a.gidx[i1 + c] : 0;
-            s = a.scale[(int64_t)gr * a.ng + g];
-            z = a.zero[(int64_t)gr * a.ng + g];
-        }
+    __shared__ int s_g[BQ_B];
+    for (int i = tid; i < BQ_B; i += nthreads) {
+        float d = (i < count) ? a.U[(int64_t)(i1 + i) * a.ldu + i1 + i] : 1.f;
+        s_rd[i] = __frcp_rn(d);
+        s_g[i] = (a.gidx && i < count) ? a.gidx[i1 + i] : 0;
+    }
+    __syncthreads();
+    // ---- stage the quantizer of every (row, column) of the block (group index from smem: one level of loads)
+    const int row0 = blockIdx.x * RPC;
+#pragma unroll 8
+    for (int idx = tid; idx < RPC * BQ_B; idx += nthreads) {
+        const int r = idx >> 7, c = idx & 127;
+        int gr = row0 + r;
+        if (gr >= a.R) gr = a.R - 1;                         // clamp: harmless duplicate of the last row
+        const int64_t o = (int64_t)gr * a.ng + s_g[c];
+        const float s = a.scale[o], z = a.zero[o];
         Ss[r * BQ_SP + c] = s;
         Zs[r * BQ_SP + c] = z;
+        Ys[r * BQ_SP + c] = __frcp_rn(s);
     }
-    // ---- W1 slice -> registers: w[kk*4+v] = W[row][i1 + kk*32 + l8*4 + v]
-    float w[16], qv[16];
-    uint32_t cpk[4] = {0u, 0u, 0u, 0u};
+    // ---- W1 slice -> registers: w[kk*4+v] = W[row][i1 + kk*16 + l4*4 + v]
+    float w[32];
+    uint32_t cpk[8];
     const bool wvec = ((a.ldw & 3) == 0) && ((i1 & 3) == 0) && ((((uintptr_t)a.W) & 15) == 0);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        int c = kk * 32 + l8 * 4;
+    for (int kk = 0; kk < 8; ++kk) {
+        int c = kk * 16 + l4 * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rvalid) {
             const float* p = a.W + (int64_t)row * a.ldw + i1 + c;
@@ -94,46 +125,50 @@ blockquant_kernel(BQArgs a) {
             }
         }
         w[kk * 4 + 0] = v.x; w[kk * 4 + 1] = v.y; w[kk * 4 + 2] = v.z; w[kk * 4 + 3] = v.w;
-        qv[kk * 4 + 0] = qv[kk * 4 + 1] = qv[kk * 4 + 2] = qv[kk * 4 + 3] = 0.f;
+        cpk[kk] = 0u;
     }
     __syncthreads();
 
-    double loss = 0.0;
+    float loss = 0.f;
     const float* srow = Ss + rl * BQ_SP;
     const float* zrow = Zs + rl * BQ_SP;
-    const int lbase = lane & ~7;
+    const float* yrow = Ys + rl * BQ_SP;
+    const int lbase = lane & ~3;
 
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
+    for (int kk = 0; kk < 8; ++kk) {
 #pragma unroll 1
-        for (int l = 0; l < 8; ++l) {
+        for (int l = 0; l < 4; ++l) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const int i = kk * 32 + l * 4 + v;
+                const int i = kk * 16 + l * 4 + v;
                 if (i < count) {                                         // block-uniform
                     const float wi = __shfl_sync(0xffffffffu, w[kk * 4 + v], lbase | l);
-                    const float d = Hs[i * BQ_B + i];
-                    const float sc = srow[i], zr = zrow[i];
+                    const float d = Hs[i * BQ_B + i], rd = s_rd[i];
+                    const float sc = srow[i], zr = zrow[i], ys = yrow[i];
                     float code, q;
                     if (a.trits) q = quant_trits(wi, sc, zr, &code);
-                    else { code = quant_code(wi, sc, zr, a.maxq); q = dequant(code, sc, zr); }
+                    else {                                               // quant.py:9-10
+                        float t = __fadd_rn(rintf(div_by_recip(wi, sc, ys)), zr);
+                        code = fminf(fmaxf(t, 0.f), a.maxq);
+                        q = dequant(code, sc, zr);
+                    }
                     const float diff = __fsub_rn(wi, q);
-                    const float err = __fdiv_rn(diff, d);                  // gptq.py:269
-                    loss += (double)__fmul_rn(err, err);      // gptq.py:267: (w-q)^2/d^2 == err^2 up to one rounding (reported scalar only)
+                    const float err = div_by_recip(diff, d, rd);           // gptq.py:269
+                    loss = fmaf(err, err, loss);                           // gptq.py:267: (w-q)^2/d^2 (reported scalar)
                     // rank-1 update of the columns this lane still owns (gptq.py:270)
 #pragma unroll
-                    for (int k2 = kk; k2 < 4; ++k2) {
-                        const float4 h = *reinterpret_cast<const float4*>(&Hs[i * BQ_B + k2 * 32 + l8 * 4]);
+                    for (int k2 = kk; k2 < 8; ++k2) {
+                        const float4 h = *reinterpret_cast<const float4*>(&Hs[i * BQ_B + k2 * 16 + l4 * 4]);
                         const float hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
                         for (int v2 = 0; v2 < 4; ++v2) {
-                            const bool upd = (k2 > kk) || (l8 > l) || (l8 == l && v2 > v);
+                            const bool upd = (k2 > kk) || (l4 > l) || (l4 == l && v2 > v);
                             if (upd) w[k2 * 4 + v2] = __fsub_rn(w[k2 * 4 + v2], __fmul_rn(err, hv[v2]));
                         }
                     }
-                    if (l8 == l) {                                       // owner keeps the results
+                    if (l4 == l) {                                       // owner keeps the results
                         w[kk * 4 + v] = err;
-                        qv[kk * 4 + v] = q;
                         cpk[kk] |= ((uint32_t)code & 0xFFu) << (8 * v);
                     }
                 }
@@ -141,40 +176,72 @@ blockquant_kernel(BQArgs a) {
         }
     }
 
-    // ---- outputs: Q, codes, Err1 (16-byte stores), loss
+    // ---- outputs: Q (recomputed from the codes with the same two roundings), codes, Err1, loss
     if (rvalid) {
         const bool qvec = ((a.ldq & 3) == 0) && ((i1 & 3) == 0) && ((((uintptr_t)a.Q) & 15) == 0);
         const bool cvec = ((a.ldc & 3) == 0) && ((i1 & 3) == 0) && ((((uintptr_t)a.codes) & 3) == 0);
+        const bool evec = ((a.lde & 3) == 0) && ((((uintptr_t)a.Err) & 15) == 0);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int c = kk * 32 + l8 * 4;
+        for (int kk = 0; kk < 8; ++kk) {
+            const int c = kk * 16 + l4 * 4;
             if (c >= count) continue;
+            float qv[4];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const float code = (float)((cpk[kk] >> (8 * v)) & 0xFFu);
+                const float sc = srow[c + v], zr = zrow[c + v];
+                if (a.trits) qv[v] = __fadd_rn(__fmul_rn(code > 1.5f ? 1.f : 0.f, sc), __fmul_rn(code < 0.5f ? 1.f : 0.f, zr));
+                else qv[v] = dequant(code, sc, zr);
+            }
             float* qp = a.Q + (int64_t)row * a.ldq + i1 + c;
             uint8_t* cp = a.codes + (int64_t)row * a.ldc + i1 + c;
             float* ep = a.Err + (int64_t)row * a.lde + c;
             if (c + 3 < count) {
-                if (qvec) *reinterpret_cast<float4*>(qp) = make_float4(qv[kk * 4], qv[kk * 4 + 1], qv[kk * 4 + 2], qv[kk * 4 + 3]);
-                else { qp[0] = qv[kk * 4]; qp[1] = qv[kk * 4 + 1]; qp[2] = qv[kk * 4 + 2]; qp[3] = qv[kk * 4 + 3]; }
+                if (qvec) *reinterpret_cast<float4*>(qp) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+                else { qp[0] = qv[0]; qp[1] = qv[1]; qp[2] = qv[2]; qp[3] = qv[3]; }
                 if (cvec) *reinterpret_cast<uint32_t*>(cp) = cpk[kk];
                 else { cp[0] = cpk[kk] & 0xFF; cp[1] = (cpk[kk] >> 8) & 0xFF; cp[2] = (cpk[kk] >> 16) & 0xFF; cp[3] = cpk[kk] >> 24; }
-                *reinterpret_cast<float4*>(ep) = make_float4(w[kk * 4], w[kk * 4 + 1], w[kk * 4 + 2], w[kk * 4 + 3]);
+                if (evec) *reinterpret_cast<float4*>(ep) = make_float4(w[kk * 4], w[kk * 4 + 1], w[kk * 4 + 2], w[kk * 4 + 3]);
+                else { ep[0] = w[kk * 4]; ep[1] = w[kk * 4 + 1]; ep[2] = w[kk * 4 + 2]; ep[3] = w[kk * 4 + 3]; }
             } else {
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
-                    if (c + v < count) { qp[v] = qv[kk * 4 + v]; cp[v] = (cpk[kk] >> (8 * v)) & 0xFF; ep[v] = w[kk * 4 + v]; }
+                    if (c + v < count) { qp[v] = qv[v]; cp[v] = (cpk[kk] >> (8 * v)) & 0xFF; ep[v] = w[kk * 4 + v]; }
             }
         }
     }
-    if (!rvalid || l8 != 0) loss = 0.0;
+    double dl = (rvalid && l4 == 0) ? (double)loss : 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
-    if (lane == 0) s_loss[warp] = loss;
+    for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o);
+    if (lane == 0) s_loss[warp] = dl;
     __syncthreads();
     if (tid == 0) {
         double t = 0.0;
-        for (int i = 0; i < BQ_THREADS / 32; ++i) t += s_loss[i];
+        for (int i = 0; i < (nthreads >> 5); ++i) t += s_loss[i];
         atomicAdd(a.loss, t * 0.5);                                      // Losses1 / 2, gptq.py:274
     }
+}
+
+// Counts (a,b) pairs for which div_by_recip(a, b, RN(1/b)) differs from div.rn.f32(a, b).
+__global__ void selftest_div_kernel(uint64_t n, uint32_t seed, int mode, unsigned long long* mismatches) {
+    uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (; idx < n; idx += stride) {
+        uint64_t x = idx * 0x9E3779B97F4A7C15ull + seed;
+        x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+        uint32_t ma = (uint32_t)x & 0x7FFFFF, mb = (uint32_t)(x >> 23) & 0x7FFFFF;
+        int ea = (int)((x >> 46) & 31) - 16, eb = (int)((x >> 51) & 31) - 16;     // exponents in [-16, 15]
+        if (mode == 1) mb = 0x7FFFFF - (mb & 0xFF);                                // significand of b near all-ones
+        if (mode == 2) mb = mb & 0xFF;                                             // significand of b near 1.0
+        float a = __uint_as_float(((uint32_t)(ea + 127) << 23) | ma);
+        float b = __uint_as_float(((uint32_t)(eb + 127) << 23) | mb);
+        if (x >> 63) a = -a;
+        if ((x >> 62) & 1) b = -b;
+        float y = __frcp_rn(b);
+        if (__float_as_uint(div_by_recip(a, b, y)) != __float_as_uint(__fdiv_rn(a, b))) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 }  // namespace gq
@@ -204,10 +271,15 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
     if (R == 0) return 0;
     cudaStream_t st = as_stream(stream);
     float* Err = static_cast<float*>(ws);
-    const size_t smem = (size_t)(BQ_B * BQ_B + 2 * BQ_ROWS * BQ_SP) * sizeof(float);
+    // one CTA per SM: slab of rows sized so that the grid fits in one wave where possible
+    int rpc = ((cdiv(R, num_sms()) + 7) / 8) * 8;
+    if (rpc < 8) rpc = 8;
+    if (rpc > BQ_MAX_ROWS) rpc = BQ_MAX_ROWS;
+    const size_t smem = (size_t)(BQ_B * BQ_B + 3 * rpc * BQ_SP) * sizeof(float);
     static bool attr_done = false;
     if (!attr_done) {
-        GQ_CUDA(cudaFuncSetAttribute(blockquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem_max = (size_t)(BQ_B * BQ_B + 3 * BQ_MAX_ROWS * BQ_SP) * sizeof(float);
+        GQ_CUDA(cudaFuncSetAttribute(blockquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         attr_done = true;
     }
     GQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
@@ -234,8 +306,8 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
         }
         float* Eblk = Err + (i1 - sb_start);
         BQArgs a{W, R, K, ldw, U, ldu, i1, count, gidx, scale, zero, ngroups, (float)maxq, maxq < 0 ? 1 : 0,
-                 Q, ldq, codes, ldc, Eblk, lde, loss};
-        blockquant_kernel<<<cdiv(R, BQ_ROWS), BQ_THREADS, smem, st>>>(a);
+                 Q, ldq, codes, ldc, Eblk, lde, loss, rpc};
+        blockquant_kernel<<<cdiv(R, rpc), rpc * 4, smem, st>>>(a);
         GQ_LAUNCHED();
         if (i2 < sb_end) {            // near: the rest of this super-block
             int rc = gemm_fp32(0, 0, R, sb_end - i2, count, -1.f, Eblk, lde, U + (int64_t)i1 * ldu + i2, ldu, 1.f,
@@ -247,5 +319,15 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
             if (rc) return rc;
         }
     }
+    return 0;
+}
+
+extern "C" int gptq_b200_selftest_div(uint64_t n, uint32_t seed, int mode, unsigned long long* mismatches, void* stream) {
+    GQ_ARG(mismatches, 4, "null");
+    GQ_ARG(mode >= 0 && mode <= 2, 3, "mode must be 0 (random), 1 (b near 2-ulp) or 2 (b near 1)");
+    cudaStream_t st = as_stream(stream);
+    GQ_CUDA(cudaMemsetAsync(mismatches, 0, sizeof(unsigned long long), st));
+    selftest_div_kernel<<<num_sms() * 8, 256, 0, st>>>(n, seed, mode, mismatches);
+    GQ_LAUNCHED();
     return 0;
 }

@@ -142,6 +142,10 @@ int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const float* U, int64
                       float norm, int grid, float maxshrink,
                       float* Q, int64_t ldq, uint8_t* codes, int64_t ldc, double* loss,
                       void* ws, size_t ws_bytes, void* stream);
+/* Device self-test of the column loop's division: counts pairs (a,b) out of n pseudo-random ones
+ * for which the hoisted-reciprocal quotient differs from div.rn.f32 (must be 0).  *mismatches is a
+ * device uint64. */
+int gptq_b200_selftest_div(uint64_t n, uint32_t seed, int mode, unsigned long long* mismatches, void* stream);
 /* gptq.py:300-305: weight_out[r, c] = (dtype) Q[r, invperm[c]]; codes_out likewise.
  * invperm may be NULL. */
 int gptq_b200_finalize(const float* Q, int64_t ldq, const uint8_t* codes, int64_t ldc,

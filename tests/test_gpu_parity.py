@@ -422,3 +422,12 @@ def test_hinv_upper_backends_agree(K):
     assert i0 == 0 and i1 == 0
     _log(test="hinv_backends", K=K, rel=O.rel_fro(U1, U0))
     assert O.rel_fro(U1, U0) < 2e-6
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_hoisted_reciprocal_division_is_exact(mode):
+    """The column loop's a/b = f(a, b, RN(1/b)) must equal div.rn.f32 bit for bit (2^31 pairs per mode)."""
+    out = torch.zeros(1, dtype=torch.int64, device=DEV)
+    _lib.check(_lib.load().gptq_b200_selftest_div(1 << 31, 12345 + mode, mode, out.data_ptr(), _lib.stream()), "selftest_div")
+    torch.cuda.synchronize()
+    assert int(out.item()) == 0
