@@ -46,6 +46,7 @@ SIGNATURES = {
     "gptq_b200_pack_codes": (_i, [_vp, _i, _i, _i64, _i, _vp, _vp]),
     "gptq_b200_pack_weights": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     "gptq_b200_unpack_codes": (_i, [_vp, _i, _i, _i, _vp, _i64, _vp]),
+    "gptq_b200_vecquant_matvec": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp]),
     "gptq_b200_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _f, _vp, _i64, _vp]),
     "gptq_b200_gemm3x": (_i, [_i, _i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _f, _vp, _i64, _vp]),
     "gptq_b200_set_gemm_backend": (_i, [_i]),

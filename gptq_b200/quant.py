@@ -224,6 +224,8 @@ class QuantLinear(nn.Module):
             if g_idx is None:
                 raise ValueError("grouped scales need g_idx")
             gi = g_idx.to(device=dev, dtype=torch.int32).contiguous()
+        if gi is not None:
+            self.g_idx = gi.to(orig)
         qweight = torch.empty((K * self.bits // 32, R), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.load().gptq_b200_pack_weights(W.data_ptr(), _lib.dt(W), R, K, W.stride(0), s2.data_ptr(),
@@ -232,9 +234,30 @@ class QuantLinear(nn.Module):
         self.qweight = qweight.to(orig)
 
     def forward(self, x):
-        # Reference: quant.py:189-203 -> quant_cuda.vecquant3matmul (single-token matvec).  The packed
-        # inference kernels are the first "next" row of SURVEY 8(f); not part of the quantization path.
-        raise NotImplementedError("packed-weight inference kernels are not part of the quantization hot path yet")
+        """quant.py:189-203: single-token matvec on the packed weights (y starts as the bias)."""
+        if x.shape[-1] == x.numel():
+            _lib.require_cuda(x, "QuantLinear.forward: x")
+            dev = x.device
+            outshape = list(x.shape)
+            outshape[-1] = self.bias.numel()
+            dtype = x.dtype
+            y = self.bias.to(device=dev, dtype=torch.float32).clone()
+            xv = x.reshape(-1).contiguous()
+            if xv.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+                xv = xv.float()
+            qw = self.qweight.to(dev)
+            s2 = self.scales.to(dev).float().reshape(self.outfeatures, -1).contiguous()
+            z2 = self.zeros.to(dev).float().reshape(self.outfeatures, -1).contiguous()
+            ng = s2.shape[1]
+            gi = getattr(self, "g_idx", None)
+            gi = None if gi is None else gi.to(device=dev, dtype=torch.int32).contiguous()
+            if ng > 1 and gi is None:
+                raise ValueError("grouped scales need g_idx")
+            _lib.check(_lib.load().gptq_b200_vecquant_matvec(xv.data_ptr(), _lib.dt(xv), qw.data_ptr(), self.outfeatures,
+                                                             self.infeatures, self.bits, s2.data_ptr(), z2.data_ptr(), ng,
+                                                             _lib.ptr(gi), 0, y.data_ptr(), _lib.stream()), "vecquant_matvec")
+            return y.to(dtype).reshape(outshape)
+        raise ValueError('Only supports a single token currently.')
 
 
 class Quant3Linear(QuantLinear):

@@ -171,6 +171,18 @@ int gptq_b200_unpack_codes(const int32_t* qweight, int R, int K, int bits,
                            uint8_t* codes, int64_t ldc, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ *     Packed-weight matvec (the consumer of the packed format; SURVEY 8f "next" #1).  Replaces
+ *     quant_cuda.vecquant3matmul / vecquant3matmul_faster (quant_cuda.cpp:15-29,
+ *     quant_cuda_kernel.cu:88-244) and the unshipped vecquant4matmul:
+ *         y[r] += sum_k (scales[r,g(k)] * code[k,r] - zeros_scaled[r,g(k)]) * x[k]
+ *     x: [K] f16/bf16/f32 (single token, like the reference); qweight: [K*bits/32, R]; y: [R] fp32,
+ *     pre-loaded with the bias by the caller.  g(k) = g_idx[k] if given, else k / groupsize.
+ * ------------------------------------------------------------------------------------------ */
+int gptq_b200_vecquant_matvec(const void* x, int dtype, const int32_t* qweight, int R, int K, int bits,
+                              const float* scales, const float* zeros_scaled, int ngroups,
+                              const int32_t* g_idx, int groupsize, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  *     fp32 GEMM used by the chain and the lazy update (exposed for tests / roofline runs):
  *     C[M,N] <- alpha * op(A) op(B) + beta * C,  op = transpose if the flag is set.
  * ------------------------------------------------------------------------------------------ */

@@ -415,6 +415,20 @@ def unpack(qweight: np.ndarray, bits: int, K: int) -> np.ndarray:
     return out.reshape(K, R)
 
 
+def vecquant_matvec(x: np.ndarray, qweight: np.ndarray, scales: np.ndarray, zeros_scaled: np.ndarray, bits: int,
+                    bias: Optional[np.ndarray] = None, g_idx: Optional[np.ndarray] = None) -> np.ndarray:
+    """quant_cuda_kernel.cu:88-165 in float64: y[c] = bias[c] + sum_k (scale[c,g]*code[k,c] - zs[c,g]) * x[k]."""
+    K = x.shape[0]
+    codes = unpack(qweight, bits, K).astype(np.float64)          # [K, R]
+    R = codes.shape[1]
+    s = scales.reshape(R, -1).astype(np.float64)
+    z = zeros_scaled.reshape(R, -1).astype(np.float64)
+    g = np.zeros(K, dtype=np.int64) if g_idx is None else np.asarray(g_idx, dtype=np.int64)
+    Wd = s[:, g].T * codes - z[:, g].T                           # [K, R]
+    y = x.astype(np.float64) @ Wd
+    return y if bias is None else y + bias.astype(np.float64)
+
+
 # --------------------------------------------------------------------------------------
 # Parity metrics (SURVEY 7.2 step 0)
 # --------------------------------------------------------------------------------------

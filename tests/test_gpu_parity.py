@@ -431,3 +431,49 @@ def test_hoisted_reciprocal_division_is_exact(mode):
     _lib.check(_lib.load().gptq_b200_selftest_div(1 << 31, 12345 + mode, mode, out.data_ptr(), _lib.stream()), "selftest_div")
     torch.cuda.synchronize()
     assert int(out.item()) == 0
+
+
+# ------------------------------------------------------------------------------------------ packed matvec
+@pytest.mark.parametrize("bits", [2, 3, 4, 8])
+@pytest.mark.parametrize("grouped", [False, True])
+@pytest.mark.parametrize("xdtype", [torch.float32, torch.float16])
+def test_quantlinear_forward_vs_oracle(bits, grouped, xdtype):
+    R, K, gs = 200, 512, 64
+    rng = np.random.default_rng(bits + 10 * grouped)
+    ng = K // gs if grouped else 1
+    codes = rng.integers(0, 2 ** bits, size=(R, K), dtype=np.uint8)
+    scales = (rng.random((R, ng)) * 0.02 + 0.005).astype(np.float32)
+    zeros = rng.integers(0, 2 ** bits, size=(R, ng)).astype(np.float32)
+    g_idx = (rng.permutation(K) // gs).astype(np.int32) if grouped else None      # act-order style arbitrary groups
+    bias = rng.standard_normal(R).astype(np.float32)
+    x = rng.standard_normal(K).astype(np.float32)
+    ql = Q.QuantLinear(bits, K, R)
+    ql.qweight = Q.pack_codes(torch.from_numpy(codes).to(DEV), bits)
+    ql.scales = torch.from_numpy(scales).to(DEV)
+    ql.zeros = torch.from_numpy(zeros * scales).to(DEV)
+    ql.bias = torch.from_numpy(bias).to(DEV)
+    if grouped:
+        ql.g_idx = torch.from_numpy(g_idx).to(DEV)
+    xt = torch.from_numpy(x).to(DEV).to(xdtype)
+    y = ql(xt.reshape(1, 1, K))
+    assert y.shape == (1, 1, R) and y.dtype == xdtype
+    want = O.vecquant_matvec(xt.float().cpu().numpy(), ql.qweight.cpu().numpy(), scales, zeros * scales, bits, bias, g_idx)
+    tol = 2e-3 if xdtype == torch.float16 else 1e-4
+    err = np.abs(y.float().cpu().numpy().reshape(-1) - want).max() / np.abs(want).max()
+    _log(test="vecquant", bits=bits, grouped=grouped, dtype=str(xdtype), rel_max=float(err))
+    assert err < tol
+    with pytest.raises(ValueError):
+        ql(torch.zeros(2, K, device=DEV))
+
+
+def test_pack_then_forward_matches_dense_layer(golden_A):
+    """Reference flow opt.py:362-373 + :440-507: fasterquant -> pack -> packed forward == dense forward of the quantized layer."""
+    z, meta = golden_A
+    c = next(c for c in meta["cases"] if c["name"] == "b3_perchannel")
+    lin, g = _run_gptq(torch.from_numpy(z["W"]), list(torch.from_numpy(z["X"])), c)
+    ql = Q.Quant3Linear(meta["K"], meta["R"])
+    ql.pack(lin, g.quantizer.scale, g.quantizer.zero)
+    x = torch.randn(1, meta["K"], device=DEV)
+    y = ql(x)
+    y_ref = x.double() @ lin.weight.data.double().t()
+    assert torch.allclose(y.double(), y_ref, rtol=1e-3, atol=1e-4)
