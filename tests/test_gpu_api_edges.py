@@ -1,0 +1,186 @@
+"""Edge cases of the reference-facing API: layer kinds, input ranks, ragged / empty batches, odd sizes,
+non-default block sizes -- every result checked against the CPU oracle."""
+import contextlib
+import copy
+import io
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import gptq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from gptq_b200.gptq import GPTQ
+    from gptq_b200 import quant as Q
+    DEV = torch.device("cuda:0")
+
+
+def _acts(T, K, seed, dtype=torch.float16):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(T, K, generator=g) * torch.exp(0.5 * torch.randn(K, generator=g))).to(dtype)
+
+
+def _gptq(layer, bits=4, **cfg):
+    g = GPTQ(layer)
+    g.quantizer = Q.Quantizer()
+    g.quantizer.configure(bits, perchannel=True, sym=cfg.get("sym", False), mse=False)
+    return g
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+@pytest.mark.parametrize("R,K", [(1, 64), (7, 100), (33, 72), (130, 1000), (64, 8)])
+def test_odd_shapes_match_oracle(R, K):
+    W = (torch.randn(R, K, generator=torch.Generator().manual_seed(R + K)) * 0.02).half()
+    X = [_acts(max(96, K) + 8 * i, K, i) for i in range(3)]              # ragged token counts, 2-D inputs, tokens >= 3K
+    lin = nn.Linear(K, R, bias=False).half().to(DEV)
+    lin.weight.data = W.to(DEV)
+    g = _gptq(lin)
+    st = O.HessianState(K)
+    for x in X:
+        g.add_batch(x.to(DEV), None)
+        O.add_batch(st, x)
+    assert g.nsamples == st.nsamples == 3
+    assert O.rel_fro(g.H.cpu(), st.H) < 1e-5
+    g.H = st.H.to(DEV).clone()                                            # identical H -> exact comparison of the solver
+    _quiet(g.fasterquant, groupsize=32 if K >= 64 else -1)
+    ref = O.fasterquant(W, st.H, O.QParams(bits=4), groupsize=32 if K >= 64 else -1)
+    bad_rows = int((g.codes.cpu() != ref.codes).any(dim=1).sum())
+    assert bad_rows <= 1, bad_rows                                        # at most one rounding-tie flip
+    if bad_rows == 0:
+        assert torch.equal(lin.weight.data.cpu(), ref.Q.half())
+
+
+def test_batched_3d_input_and_empty_batch():
+    K, R = 128, 16
+    lin = nn.Linear(K, R, bias=False).half().to(DEV)
+    g = _gptq(lin)
+    st = O.HessianState(K)
+    x = torch.stack([_acts(64, K, i) for i in range(4)])                  # [4, 64, K]: tmp = 4 sequences at once (gptq.py:44)
+    g.add_batch(x.to(DEV), None)
+    O.add_batch(st, x)
+    g.add_batch(torch.empty(1, 0, K, dtype=torch.float16, device=DEV), None)   # empty batch still counts one sample
+    O.add_batch(st, torch.empty(1, 0, K, dtype=torch.float16))
+    assert g.nsamples == st.nsamples == 5
+    assert O.rel_fro(g.H.cpu(), st.H) < 1e-5
+    # reading H in the middle of calibration must not disturb the accumulation
+    y = _acts(64, K, 9)
+    g.add_batch(y.to(DEV), None)
+    O.add_batch(st, y)
+    assert O.rel_fro(g.H.cpu(), st.H) < 1e-5
+    assert torch.allclose(g.input.cpu(), st.last_input_mean, rtol=1e-4, atol=1e-6)
+
+
+def test_bf16_model_and_activations():
+    K, R = 256, 48
+    W = (torch.randn(R, K, generator=torch.Generator().manual_seed(0)) * 0.02).bfloat16()
+    lin = nn.Linear(K, R, bias=False).bfloat16().to(DEV)
+    lin.weight.data = W.to(DEV)
+    g = _gptq(lin)
+    st = O.HessianState(K)
+    for i in range(3):
+        x = _acts(128, K, i, torch.bfloat16)
+        g.add_batch(x.to(DEV).unsqueeze(0), None)
+        O.add_batch(st, x.unsqueeze(0))
+    assert O.rel_fro(g.H.cpu(), st.H) < 1e-5
+    g.H = st.H.to(DEV).clone()
+    _quiet(g.fasterquant, groupsize=128, actorder=True, static_groups=True)
+    ref = O.fasterquant(W, st.H, O.QParams(bits=4), groupsize=128, actorder=True, static_groups=True)
+    assert lin.weight.dtype == torch.bfloat16
+    assert torch.equal(g.codes.cpu(), ref.codes)
+    assert torch.equal(lin.weight.data.cpu(), ref.Q.bfloat16())
+
+
+def test_fp32_activations_use_exact_fp32_path():
+    K, R = 96, 8
+    lin = nn.Linear(K, R, bias=False).to(DEV)
+    g = _gptq(lin)
+    st = O.HessianState(K)
+    for i in range(2):
+        x = _acts(80, K, i, torch.float32)
+        g.add_batch(x.to(DEV), None)
+        O.add_batch(st, x)
+    assert O.rel_fro(g.H.cpu(), st.H) < 2e-6
+
+
+def test_conv1d_layer_is_transposed_like_the_reference():
+    import transformers
+    K, R = 128, 40
+    conv = transformers.Conv1D(R, K)                                      # weight stored [K, R] (gptq.py:31-32)
+    conv.weight.data = (torch.randn(K, R, generator=torch.Generator().manual_seed(1)) * 0.02)
+    conv = conv.half().to(DEV)
+    W = conv.weight.data.t().cpu()
+    g = _gptq(conv)
+    assert (g.rows, g.columns) == (R, K)
+    st = O.HessianState(K)
+    x = _acts(200, K, 3)
+    g.add_batch(x.to(DEV).unsqueeze(0), None)
+    O.add_batch(st, x.unsqueeze(0))
+    g.H = st.H.to(DEV).clone()
+    _quiet(g.fasterquant)
+    ref = O.fasterquant(W, st.H, O.QParams(bits=4))
+    assert conv.weight.shape == (K, R)
+    assert torch.equal(conv.weight.data.cpu(), ref.Q.half().t())
+
+
+def test_conv2d_layer_unfolds_patches():
+    conv = nn.Conv2d(4, 6, kernel_size=3, padding=1, bias=False).half().to(DEV)
+    g = _gptq(conv)
+    assert (g.rows, g.columns) == (6, 36)
+    x = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(0)).half()
+    g.add_batch(x.to(DEV), None)
+    unfold = nn.Unfold(3, padding=1)
+    cols = unfold(x.float()).permute([1, 0, 2]).flatten(1)                # gptq.py:50-58: [K, tokens]
+    want = (2.0 / 2) * (cols.double() @ cols.double().t())
+    assert O.rel_fro(g.H.cpu(), want) < 1e-5
+    _quiet(g.fasterquant)
+    assert conv.weight.shape == (6, 4, 3, 3) and conv.weight.dtype == torch.float16
+
+
+@pytest.mark.parametrize("blocksize", [32, 64, 100])
+def test_non_default_blocksize(blocksize):
+    K, R = 256, 32
+    W = (torch.randn(R, K, generator=torch.Generator().manual_seed(5)) * 0.02).half()
+    lin = nn.Linear(K, R, bias=False).half().to(DEV)
+    lin.weight.data = W.to(DEV)
+    g = _gptq(lin, bits=3)
+    st = O.HessianState(K)
+    x = _acts(600, K, 1)
+    g.add_batch(x.to(DEV), None)
+    O.add_batch(st, x)
+    g.H = st.H.to(DEV).clone()
+    _quiet(g.fasterquant, blocksize=blocksize, groupsize=64)
+    ref = O.fasterquant(W, st.H, O.QParams(bits=3), blocksize=blocksize, groupsize=64)
+    agree = O.code_agreement(g.codes.cpu(), ref.codes)
+    assert agree >= 0.999
+
+
+def test_quantizer_survives_deepcopy_cpu_and_state_dict():
+    q = Q.Quantizer()
+    q.configure(4, perchannel=True, sym=False, mse=False)
+    W = torch.randn(8, 64, device=DEV)
+    q.find_params(W)
+    q2 = copy.deepcopy(q).cpu()
+    assert q2.scale.device.type == "cpu" and torch.equal(q2.scale, q.scale.cpu())
+    assert set(q.state_dict()) == {"maxq", "scale", "zero"}
+    assert bool(q.ready()) and bool(q.enabled())
+    xq = q.quantize(W)
+    assert torch.equal(xq.cpu(), O.quantize(W.cpu(), q2.scale, q2.zero, 15))
+
+
+def test_rtn_baseline_matches_reference_semantics():
+    """opt.py:292-300: find_params on the whole weight, then quantize()."""
+    W = (torch.randn(40, 96, generator=torch.Generator().manual_seed(2)) * 0.05)
+    q = Q.Quantizer()
+    q.configure(3, perchannel=True, sym=True, mse=False)
+    q.find_params(W.to(DEV), weight=True)
+    got = Q.quantize(W.to(DEV), q.scale, q.zero, q.maxq)
+    qp = O.QParams(bits=3, sym=True)
+    s, z = O.find_params(W, qp)
+    assert torch.equal(got.cpu(), O.quantize(W, s, z, qp.maxq))
