@@ -48,6 +48,8 @@ torch.backends.cudnn.allow_tf32 = False
 STAGE_SAMPLES = int(os.environ.get("GPTQ_B200_STAGE_SAMPLES", "16"))
 CHUNK_TOKENS = int(os.environ.get("GPTQ_B200_CHUNK_TOKENS", "0"))     # 0 = library default
 EMPTY_CACHE_ON_FREE = os.environ.get("GPTQ_B200_EMPTY_CACHE", "0") == "1"
+CHAIN_MEMO = os.environ.get("GPTQ_B200_CHAIN_MEMO", "1") == "1"
+_CHAIN_MEMO = {}          # (device, Kp) -> (A as handed to the chain, U, info); at most one entry
 
 
 # Optional per-call device timing: set ``gptq_b200.gptq.PROFILE = []`` and every C-ABI hot call appends
@@ -87,6 +89,7 @@ def syrk_issued_flops(K: int, tokens: int) -> float:
 class GPTQ:
 
     def __init__(self, layer):
+        _CHAIN_MEMO.clear()            # a new calibration round starts: drop the previous round's chain memo
         self.layer = layer
         self.dev = self.layer.weight.device
         _lib.require_cuda(layer.weight, "GPTQ: layer.weight")
@@ -296,14 +299,31 @@ class GPTQ:
                                                 st), "hessian_gather")
         del H
         _p0.__exit__()
-        info = torch.zeros(1, device=dev, dtype=torch.int32)
-        nws = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
-        ws = torch.empty(nws, device=dev, dtype=torch.uint8)
-        U = torch.empty((Kp, Kp), **f32)
-        with _prof("hinv_upper", 2.0 / 3.0 * Kp ** 3):
-            _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, U.data_ptr(), Kp, info.data_ptr(), ws.data_ptr(), nws,
-                                                st), "hinv_upper")
-        del ws, A
+        # Linears of one subset that see the same activations (q/k/v, gate/up) reach this point with bit-identical A.
+        # The chain is a pure function of A, so it is computed once per distinct A: the candidate is compared with the
+        # previous input EXACTLY (torch.equal, on device); the memo lives until the next GPTQ object is constructed
+        # (= the next calibration round), so nothing is ever reused across layers, subsets or benchmark steps.
+        hit = None
+        if CHAIN_MEMO:
+            ent = _CHAIN_MEMO.get((dev, Kp))
+            if ent is not None and torch.equal(A, ent[0]):
+                hit = ent
+        if hit is not None:
+            _, U, info = hit
+            del A
+        else:
+            A_in = A.clone() if CHAIN_MEMO else None
+            info = torch.zeros(1, device=dev, dtype=torch.int32)
+            nws = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
+            ws = torch.empty(nws, device=dev, dtype=torch.uint8)
+            U = torch.empty((Kp, Kp), **f32)
+            with _prof("hinv_upper", 2.0 / 3.0 * Kp ** 3):
+                _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, U.data_ptr(), Kp, info.data_ptr(), ws.data_ptr(),
+                                                    nws, st), "hinv_upper")
+            del ws, A
+            if CHAIN_MEMO:
+                _CHAIN_MEMO.clear()
+                _CHAIN_MEMO[(dev, Kp)] = (A_in, U, info)
 
         if not q.ready():                               # gptq.py:181-185
             q.find_params(Wp)

