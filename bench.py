@@ -235,6 +235,9 @@ def quantize_layer(dev, acts, weights, world, from_host):
             bufs = [torch.empty(X.shape[1:], dtype=X.dtype, device=dev) for _ in range(2)]
             ready = [torch.cuda.Event(), torch.cuda.Event()]
             freed = [torch.cuda.Event(), torch.cuda.Event()]
+            # the buffers come from the main stream's allocator pool: the copy stream may only touch them after
+            # everything already queued on the main stream (previous users of that memory) has run
+            cs.wait_stream(cur)
             with torch.cuda.stream(cs):
                 bufs[0].copy_(X[0], non_blocking=True)
                 ready[0].record(cs)
@@ -252,11 +255,17 @@ def quantize_layer(dev, acts, weights, world, from_host):
                 for g in gs:
                     g.add_batch(xj, None)
                 freed[b].record(cur)
+            cur.wait_stream(cs)
         else:
             for j in range(X.shape[0]):
                 xj = X[j].unsqueeze(0)
                 for g in gs:                              # the forward hooks of q/k/v see the same tensor
                     g.add_batch(xj, None)
+        if os.environ.get("GPTQ_B200_DEBUG_SYNC"):
+            torch.cuda.synchronize()
+            fin = [bool(torch.isfinite(g.raw_accumulator()).all()) for g in gs]
+            print("debug: add_batch phase ok", [LINEARS[li][0] for li in subset], "S finite:", fin,
+                  "X finite:", bool(torch.isfinite(X.float()).all()) if from_host else "-", file=sys.stderr)
         for g in gs:
             if world > 1:
                 gd.allreduce_hessian(g)
@@ -373,6 +382,8 @@ def run_ours(args):
                "d2h_bytes_per_step": d2h * world, "ms_per_step": ems / e_steps, "steps": e_steps}
         del acts_h, weights_h
     except Exception as ex:  # pinned allocation can fail on small hosts; report instead of hiding
+        import traceback
+        traceback.print_exc(file=sys.stderr)
         e2e = {"value": None, "unit": "Mweights/s", "error": repr(ex)}
 
     if rank == 0:

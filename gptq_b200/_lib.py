@@ -28,6 +28,7 @@ SIGNATURES = {
     "gptq_b200_syrk_accum_simt": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _f, _f, _vp]),
     "gptq_b200_symmetrize": (_i, [_vp, _i, _i64, _vp]),
     "gptq_b200_stage_input": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _vp]),
+    "gptq_b200_compare_rows": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp, _vp]),
     "gptq_b200_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp, _vp]),
     "gptq_b200_weights_prepare": (_i, [_vp, _i, _i, _i, _i64, _vp, _vp, _i64, _vp]),
     "gptq_b200_dead_columns": (_i, [_vp, _i, _i64, _vp, _vp]),

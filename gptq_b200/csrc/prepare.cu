@@ -133,6 +133,31 @@ __global__ void stage_kernel(const T* __restrict__ src, int64_t tokens, int K, i
         dst[t * ldd + c] = (c < K) ? src[t * lds + c] : from_f32<T>(0.f);
 }
 
+// ------------------------------------------------------------------ exact (bitwise) comparison of two 16-bit batches
+// flag |= 1 when any element differs.  Used to verify that a batch handed to a second GPTQ object is the very
+// batch already staged by the first one before their Hessian accumulators are shared (gptq.py:38-65 computes
+// the same H for q/k/v three times; we compute it once, but only for provably identical inputs).
+__global__ void compare_rows_kernel(const uint16_t* __restrict__ a, int64_t lda, const uint16_t* __restrict__ b, int64_t ldb,
+                                    int64_t tokens, int K, int vec, int32_t* __restrict__ flag) {
+    bool diff = false;
+    if (vec) {                                   // K % 8 == 0, both pitches % 8 == 0, both bases 16-byte aligned
+        const int kv = K >> 3;
+        for (int64_t t = blockIdx.y; t < tokens; t += gridDim.y) {
+            const uint4* pa = reinterpret_cast<const uint4*>(a + t * lda);
+            const uint4* pb = reinterpret_cast<const uint4*>(b + t * ldb);
+            for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < kv; c += gridDim.x * blockDim.x) {
+                const uint4 x = pa[c], y = pb[c];
+                diff |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+            }
+        }
+    } else {
+        for (int64_t t = blockIdx.y; t < tokens; t += gridDim.y)
+            for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < K; c += gridDim.x * blockDim.x)
+                diff |= a[t * lda + c] != b[t * ldb + c];
+    }
+    if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
 // ------------------------------------------------------------------ Q[:, invperm] + cast
 template <typename T>
 __global__ void finalize_kernel(const float* __restrict__ Q, int64_t ldq, const uint8_t* __restrict__ codes, int64_t ldc, int R,
@@ -254,6 +279,20 @@ extern "C" int gptq_b200_stage_input(const void* src, int dtype, int64_t tokens,
     dim3 g(cdiv(ld_dst, 256), (unsigned)(tokens > 4096 ? 4096 : tokens));
     if (dtype == GPTQ_B200_F16) stage_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, tokens, K, ld_src, (__half*)dst, ld_dst);
     else stage_kernel<__nv_bfloat16><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, tokens, K, ld_src, (__nv_bfloat16*)dst, ld_dst);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_compare_rows(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t tokens, int K,
+                                      int32_t* flag, void* stream) {
+    GQ_ARG(a, 1, "null"); GQ_ARG(lda >= K, 2, "lda<K"); GQ_ARG(b, 3, "null"); GQ_ARG(ldb >= K, 4, "ldb<K");
+    GQ_ARG(tokens >= 0, 5, "tokens<0"); GQ_ARG(K > 0, 6, "K<=0"); GQ_ARG(flag, 7, "null");
+    if (tokens == 0) return 0;
+    const int vec = (K % 8 == 0) && (lda % 8 == 0) && (ldb % 8 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    const int per_row = vec ? K / 8 : K;
+    dim3 g(cdiv(per_row, 256) > 8 ? 8 : cdiv(per_row, 256), (unsigned)(tokens > 2048 ? 2048 : tokens));
+    compare_rows_kernel<<<g, 256, 0, as_stream(stream)>>>((const uint16_t*)a, lda, (const uint16_t*)b, ldb, tokens, K, vec, flag);
     GQ_LAUNCHED();
     return 0;
 }

@@ -43,12 +43,21 @@ def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def allreduce_hessian(gptq, group=None) -> None:
-    """Exchange #1: sum the partial accumulators and sample counts of all ranks (in place)."""
+    """Exchange #1: sum the partial accumulators and sample counts of all ranks (in place).  Linears that share one
+    accumulator (same activations: q/k/v, gate/up) are reduced once; the later ones only pick up the global count."""
+    acc = getattr(gptq, "_acc", None)
+    if acc is not None and acc.reduced:
+        gptq.nsamples = acc.count
+        return
     S = gptq.raw_accumulator()
     allreduce_sum_(S, group)
     n = torch.tensor([gptq.nsamples], device=S.device, dtype=torch.int64)
     allreduce_sum_(n, group)
     gptq.nsamples = int(n.item())
+    acc = getattr(gptq, "_acc", None)
+    if acc is not None:
+        acc.count = gptq.nsamples
+        acc.reduced = True
 
 
 def allgather_rows(local: torch.Tensor, rows_total: int, group=None) -> torch.Tensor:

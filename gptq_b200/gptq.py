@@ -24,6 +24,7 @@ import copy
 import math
 import os
 import time
+import weakref
 
 import torch
 import torch.nn as nn
@@ -48,8 +49,13 @@ torch.backends.cudnn.allow_tf32 = False
 STAGE_SAMPLES = int(os.environ.get("GPTQ_B200_STAGE_SAMPLES", "16"))
 CHUNK_TOKENS = int(os.environ.get("GPTQ_B200_CHUNK_TOKENS", "0"))     # 0 = library default
 EMPTY_CACHE_ON_FREE = os.environ.get("GPTQ_B200_EMPTY_CACHE", "0") == "1"
-CHAIN_MEMO = os.environ.get("GPTQ_B200_CHAIN_MEMO", "1") == "1"
-_CHAIN_MEMO = {}          # (device, Kp) -> (A as handed to the chain, U, info); at most one entry
+# Linears that receive the very same activation tensor (q/k/v, gate/up: their forward hooks see one tensor) share ONE
+# Hessian accumulator, ONE prologue and ONE inverse-Cholesky chain; the reference recomputes all three per linear
+# (gptq.py:38-65, 143-180).  A batch is shared only when it is the same memory (pointer, shape, strides, dtype, with the
+# first holder keeping the tensor alive) AND, with SHARE_VERIFY, bit-identical to the staged copy (device-side compare,
+# checked at fasterquant's own host sync: a mismatch raises instead of producing a different result).
+SHARE_H = os.environ.get("GPTQ_B200_SHARE_H", "1") == "1"
+SHARE_VERIFY = os.environ.get("GPTQ_B200_SHARE_VERIFY", "1") == "1"
 
 
 # Optional per-call device timing: set ``gptq_b200.gptq.PROFILE = []`` and every C-ABI hot call appends
@@ -75,6 +81,18 @@ class _prof:
         return False
 
 
+_DEBUG_SYNC = os.environ.get("GPTQ_B200_DEBUG_SYNC", "0") == "1"
+
+
+def _dbg(tag):
+    """GPTQ_B200_DEBUG_SYNC=1: synchronize after every device step so an asynchronous fault is attributed to it."""
+    if _DEBUG_SYNC:
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:      # pragma: no cover
+            raise RuntimeError(f"device fault surfaced after step '{tag}': {e}") from e
+
+
 def _round_up(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
@@ -86,10 +104,212 @@ def syrk_issued_flops(K: int, tokens: int) -> float:
     return 2.0 * tiles * 128 * 256 * tokens
 
 
+_JOINABLE = {}            # (device, batch identity) -> weakref(_Accumulator that has absorbed exactly that one batch)
+
+
+def _batch_key(x):
+    return (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype)
+
+
+class _Accumulator:
+    """Unscaled Hessian accumulator S = sum_tokens x x^T of ONE activation stream (gptq.py:38-65 in closed form),
+    its staging slab, and -- once a member ran ``fasterquant`` -- the finished H with the prologue / chain results
+    that only depend on H.  Several GPTQ objects (``members``) may hold the same accumulator."""
+
+    def __init__(self, K, dev):
+        self.K, self.dev = K, dev
+        self.S = None                  # [K,K] fp32, tiles touching the lower triangle valid
+        self.stage = None              # [cap_tokens, roundup(K,8)] staging slab
+        self.staged = 0
+        self.ws = None
+        self.count = 0                 # samples absorbed (the reference's nsamples)
+        self.batches = 0
+        self.members = 1
+        self.key = None                # identity of the most recent batch ...
+        self.ref = None                # ... and the tensor itself: while it is held its memory cannot be recycled
+        self.first_key = None
+        self.last_tmp = 0
+        self.last_tokens = 0
+        self.last_in_slab = False      # the most recent batch sits contiguously at the end of the slab
+        self.last = None               # (view of the last batch, count at that time) for GPTQ.input
+        self.flag = None               # device int32, set by compare_rows when a shared batch was NOT identical
+        self.reduced = False           # dist.allreduce_hessian already summed S over the ranks
+        self.sealed = False
+        self.n_final = None
+        self.H = None                  # (2/n) S, mirrored, dead diagonal fixed -- after seal()
+        self.dead = None
+        self.solves = {}               # (percdamp, actorder) -> prologue + chain results
+
+    # -------------------------------------------------------------- accumulate
+    def absorb(self, x, tmp, key, joinable):
+        if self.sealed:
+            raise RuntimeError("GPTQ.add_batch: this Hessian was already consumed by fasterquant of a linear sharing it")
+        lib = _lib.load()
+        K = self.K
+        if self.S is None:
+            self.S = torch.zeros((K, K), device=self.dev, dtype=torch.float32)
+        self.count += tmp
+        self.batches += 1
+        self.key, self.ref, self.last_tmp = key, x, tmp
+        if self.batches == 1 and joinable:
+            self.first_key = (self.dev, key)
+            _JOINABLE[self.first_key] = weakref.ref(self)
+        elif self.first_key is not None:
+            self._unregister()
+        tokens = x.shape[0]
+        self.last_tokens = tokens
+        if x.dtype == torch.float32:
+            # fp32 activations: exact fp32 CUDA-core path (the tensor path takes 16-bit operands)
+            self.flush()
+            xc = x.contiguous()
+            _lib.check(lib.gptq_b200_syrk_accum_simt(xc.data_ptr(), _lib.F32, tokens, K, xc.stride(0), self.S.data_ptr(), K,
+                                                     1.0, 1.0, _lib.stream()), "syrk_accum_simt")
+            self.last = (xc, self.count)
+            self.last_in_slab = False
+            return
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        if self.stage is None or self.stage.dtype != x.dtype:
+            self.flush()
+            cap = max(tokens, 1) * max(STAGE_SAMPLES, 1)
+            self.stage = torch.empty((cap, _round_up(K, 8)), device=self.dev, dtype=x.dtype)
+        cap = self.stage.shape[0]
+        if tokens <= cap and self.staged + tokens > cap:
+            self.flush()                                   # keep a batch contiguous in the slab
+        in_slab = tokens <= cap
+        done = 0
+        while done < tokens:
+            if self.staged == cap:
+                self.flush()
+            n = min(tokens - done, cap - self.staged)
+            dst = self.stage[self.staged:self.staged + n]
+            src = x[done:done + n]
+            _lib.check(lib.gptq_b200_stage_input(src.data_ptr(), _lib.dt(src), n, K, src.stride(0), dst.data_ptr(),
+                                                 dst.stride(0), _lib.stream()), "stage_input")
+            self.last = (dst[:, :K], self.count)
+            self.staged += n
+            done += n
+        self.last_in_slab = in_slab
+
+    def verify(self, x):
+        """Device-side proof that `x` is bit-identical to the batch staged last (result read at fasterquant's sync)."""
+        if not SHARE_VERIFY:
+            return
+        if self.flag is None:
+            self.flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
+        ref = self.stage[self.staged - self.last_tokens:self.staged]
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        _lib.check(_lib.load().gptq_b200_compare_rows(x.data_ptr(), x.stride(0), ref.data_ptr(), ref.stride(0), x.shape[0],
+                                                      self.K, self.flag.data_ptr(), _lib.stream()), "compare_rows")
+
+    def flush(self):
+        self.last_in_slab = False
+        if self.stage is None or self.staged == 0:
+            return
+        lib = _lib.load()
+        K = self.K
+        need = lib.gptq_b200_syrk_workspace_bytes(K, self.staged)
+        if need and (self.ws is None or self.ws.numel() < need):
+            self.ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
+        with _prof("syrk", syrk_issued_flops(K, self.staged)):
+            _lib.check(lib.gptq_b200_syrk_accum(self.stage.data_ptr(), _lib.dt(self.stage), self.staged, K,
+                                                self.stage.stride(0), self.S.data_ptr(), K, 1.0, 1.0, CHUNK_TOKENS,
+                                                _lib.ptr(self.ws) if need else 0, need, _lib.stream()), "syrk_accum")
+        self.staged = 0
+
+    def _unregister(self):
+        if self.first_key is not None:
+            ent = _JOINABLE.get(self.first_key)
+            if ent is not None and ent() in (self, None):
+                del _JOINABLE[self.first_key]
+            self.first_key = None
+
+    # -------------------------------------------------------------- read / consume
+    def materialize(self, n):
+        """A private full symmetric copy of (2/n) S -- what gptq.py:59-65 maintains as self.H."""
+        if self.sealed:
+            H = self.H.clone()
+            if self.n_final and n and n != self.n_final:
+                H.mul_(self.n_final / n)
+            H.diagonal()[self.dead.bool()] = 0             # undo the dead-column fix seal() applied (gptq.py:144)
+            return H
+        if self.S is None:
+            return torch.zeros((self.K, self.K), device=self.dev, dtype=torch.float32)
+        self.flush()
+        H = self.S.clone()
+        _lib.check(_lib.load().gptq_b200_symmetrize(H.data_ptr(), self.K, self.K, _lib.stream()), "symmetrize")
+        if n > 0:
+            H.mul_(2.0 / n)
+        return H
+
+    def seal(self, n):
+        """Finish H in place (mirror, scale by 2/n), once; later members get the same tensor."""
+        if self.sealed:
+            if n != self.n_final:
+                raise RuntimeError(f"fasterquant: shared Hessian was finished with nsamples={self.n_final}, "
+                                   f"this linear has nsamples={n}")
+            return self.H
+        lib = _lib.load()
+        K = self.K
+        if self.S is None:
+            self.S = torch.zeros((K, K), device=self.dev, dtype=torch.float32)
+        self.flush()
+        self._unregister()
+        H = self.S
+        _lib.check(lib.gptq_b200_symmetrize(H.data_ptr(), K, K, _lib.stream()), "symmetrize")
+        if n > 0:
+            H.mul_(2.0 / n)
+        self.dead = torch.empty(K, device=self.dev, dtype=torch.uint8)
+        _lib.check(lib.gptq_b200_dead_columns(H.data_ptr(), K, K, self.dead.data_ptr(), _lib.stream()), "dead_columns")
+        self.H, self.S, self.n_final, self.sealed = H, None, n, True
+        self.stage = self.ws = self.ref = self.last = None
+        return H
+
+
+def _solve_hessian(H, K, percdamp, actorder, dead=None):
+    """fasterquant's H-only part (gptq.py:143-144, 165-180): dead columns, damp, act-order permutation and the
+    inverse-Cholesky chain.  H's dead diagonal entries are set to 1 in place; returns a dict of device tensors."""
+    lib = _lib.load()
+    st = _lib.stream()
+    dev = H.device
+    f32 = dict(device=dev, dtype=torch.float32)
+    with _prof("prologue"):
+        if dead is None:
+            dead = torch.empty(K, device=dev, dtype=torch.uint8)
+            _lib.check(lib.gptq_b200_dead_columns(H.data_ptr(), K, K, dead.data_ptr(), st), "dead_columns")
+        _dbg("dead_columns")
+        diag = torch.empty(K, **f32)
+        damp = torch.empty(1, **f32)
+        ndead = torch.empty(1, device=dev, dtype=torch.int32)
+        _lib.check(lib.gptq_b200_hessian_prepare(H.data_ptr(), K, K, float(percdamp), diag.data_ptr(), damp.data_ptr(),
+                                                 ndead.data_ptr(), st), "hessian_prepare")
+        _dbg("hessian_prepare")
+        perm = invperm = None
+        if actorder:                                    # gptq.py:165-169
+            perm = torch.empty(K, device=dev, dtype=torch.int32)
+            invperm = torch.empty(K, device=dev, dtype=torch.int32)
+            _lib.check(lib.gptq_b200_argsort_desc(diag.data_ptr(), K, perm.data_ptr(), invperm.data_ptr(), st), "argsort")
+            _dbg("argsort")
+        Kp = _round_up(K, 128)                          # gptq.py:174-180
+        A = torch.empty((Kp, Kp), **f32)
+        _lib.check(lib.gptq_b200_hessian_gather(H.data_ptr(), K, K, _lib.ptr(perm), damp.data_ptr(), A.data_ptr(), Kp, Kp,
+                                                st), "hessian_gather")
+        _dbg("hessian_gather")
+    info = torch.zeros(1, device=dev, dtype=torch.int32)
+    nws = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
+    ws = torch.empty(nws, device=dev, dtype=torch.uint8)
+    U = torch.empty((Kp, Kp), **f32)
+    with _prof("hinv_upper", 2.0 / 3.0 * Kp ** 3):
+        _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, U.data_ptr(), Kp, info.data_ptr(), ws.data_ptr(),
+                                            nws, st), "hinv_upper")
+    _dbg("hinv_upper")
+    return dict(dead=dead, perm=perm, invperm=invperm, U=U, info=info, Kp=Kp)
+
+
 class GPTQ:
 
     def __init__(self, layer):
-        _CHAIN_MEMO.clear()            # a new calibration round starts: drop the previous round's chain memo
         self.layer = layer
         self.dev = self.layer.weight.device
         _lib.require_cuda(layer.weight, "GPTQ: layer.weight")
@@ -103,13 +323,9 @@ class GPTQ:
         self.columns = W.shape[1]
         self.nsamples = 0
         self.quantizer = None
-        # unscaled accumulator S = sum_tokens x x^T (fp32, tiles touching the lower triangle valid)
-        self._S = torch.zeros((self.columns, self.columns), device=self.dev, dtype=torch.float32)
-        self._H = None                 # materialised (2/n)*S, full symmetric
-        self._stage = None             # [cap_tokens, ld] staging slab
-        self._staged = 0
-        self._last = None              # (view of the last batch in the slab, nsamples at that time)
-        self._ws = None
+        self._acc = None               # _Accumulator (allocated with the first batch; may be shared, see SHARE_H)
+        self._H = None                 # materialised (2/n)*S, full symmetric, or a user-provided H
+        self._consumed = False
 
     # ------------------------------------------------------------------ Hessian (gptq.py:38-65)
     def add_batch(self, inp, out):
@@ -129,76 +345,94 @@ class GPTQ:
             inp = unfold(inp).permute([1, 0, 2]).flatten(1).t()   # [tokens, K]
         if inp.shape[-1] != self.columns:
             raise ValueError(f"add_batch: expected {self.columns} input features, got {inp.shape[-1]}")
-        self.nsamples += tmp
+        if inp.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+            raise TypeError(f"unsupported dtype {inp.dtype}")
+        if self._consumed:
+            raise RuntimeError("add_batch: H was already consumed by fasterquant or freed")
         self._H = None
-        if inp.dtype == torch.float32:
-            # fp32 activations: exact fp32 CUDA-core path (the tensor path takes 16-bit operands)
-            self._flush()
-            x = inp.contiguous()
-            _lib.check(_lib.load().gptq_b200_syrk_accum_simt(x.data_ptr(), _lib.F32, x.shape[0], self.columns, x.stride(0),
-                                                             self._S.data_ptr(), self.columns, 1.0, 1.0, _lib.stream()),
-                       "syrk_accum_simt")
-            self._last = (x, self.nsamples)
-            return
-        self._stage_tokens(inp)
+        x = inp
+        key = _batch_key(x)
+        shareable = SHARE_H and x.dtype != torch.float32 and x.shape[0] > 0
+        acc = self._acc
+        if acc is None:                                           # first batch: the same tensor may already be staged
+            if shareable and self.nsamples == 0:
+                ent = _JOINABLE.get((self.dev, key))
+                cand = ent() if ent is not None else None
+                if (cand is not None and cand.K == self.columns and cand.count == tmp and cand.batches == 1
+                        and cand.last_in_slab and not cand.sealed):
+                    cand.members += 1
+                    cand.verify(x)
+                    self._acc = cand
+                    self.nsamples += tmp
+                    return
+            acc = self._acc = _Accumulator(self.columns, self.dev)
+            acc.count = self.nsamples                             # (non-zero only if the caller preset nsamples)
+        elif acc.members > 1:
+            if shareable and acc.key == key and acc.count == self.nsamples + tmp and acc.last_in_slab:
+                acc.verify(x)                                     # a sibling staged this very batch already
+                self.nsamples += tmp
+                return
+            if acc.count != self.nsamples:                        # siblings moved on with a different batch
+                self._fork()
+                acc = self._acc
+        acc.absorb(x, tmp, key, shareable)
+        self.nsamples += tmp
 
-    def _stage_tokens(self, x):
-        lib = _lib.load()
-        K = self.columns
-        tokens = x.shape[0]
-        if x.stride(-1) != 1:
-            x = x.contiguous()
-        if self._stage is None or self._stage.dtype != x.dtype:
-            self._flush()
-            ld = _round_up(K, 8)
-            cap = max(tokens, 1) * max(STAGE_SAMPLES, 1)
-            self._stage = torch.empty((cap, ld), device=self.dev, dtype=x.dtype)
-        cap = self._stage.shape[0]
-        done = 0
-        while done < tokens:
-            if self._staged == cap:
-                self._flush()
-            n = min(tokens - done, cap - self._staged)
-            dst = self._stage[self._staged:self._staged + n]
-            src = x[done:done + n]
-            _lib.check(lib.gptq_b200_stage_input(src.data_ptr(), _lib.dt(src), n, K, src.stride(0), dst.data_ptr(),
-                                                 dst.stride(0), _lib.stream()), "stage_input")
-            self._last = (dst[:, :K], self.nsamples)
-            self._staged += n
-            done += n
+    def _fork(self):
+        """Leave a shared accumulator, taking a private copy of the state that matches THIS object's history."""
+        acc = self._acc
+        if acc.sealed:
+            raise RuntimeError("GPTQ: the shared Hessian was already consumed by a sibling's fasterquant")
+        if acc.count == self.nsamples:
+            keep = acc.staged
+        elif acc.count == self.nsamples + acc.last_tmp and acc.last_in_slab:
+            keep = acc.staged - acc.last_tokens                   # everything but the batch we did not receive
+        else:
+            raise RuntimeError("GPTQ: linears sharing a Hessian accumulator received different batches and the common "
+                               "state can no longer be separated; set GPTQ_B200_SHARE_H=0")
+        new = _Accumulator(acc.K, acc.dev)
+        new.S = acc.S.clone() if acc.S is not None else None
+        if acc.stage is not None:
+            new.stage = torch.empty_like(acc.stage)
+            if keep > 0:
+                new.stage[:keep].copy_(acc.stage[:keep])
+            new.staged = keep
+        new.count = self.nsamples
+        new.batches = max(acc.batches, 2)
+        new.flag = acc.flag
+        acc.members -= 1
+        self._acc = new
 
-    def _flush(self):
-        if self._stage is None or self._staged == 0:
-            return
-        lib = _lib.load()
-        K = self.columns
-        need = lib.gptq_b200_syrk_workspace_bytes(K, self._staged)
-        if need and (self._ws is None or self._ws.numel() < need):
-            self._ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        with _prof("syrk", syrk_issued_flops(K, self._staged)):
-            _lib.check(lib.gptq_b200_syrk_accum(self._stage.data_ptr(), _lib.dt(self._stage), self._staged, K,
-                                                self._stage.stride(0), self._S.data_ptr(), K, 1.0, 1.0, CHUNK_TOKENS,
-                                                _lib.ptr(self._ws) if need else 0, need, _lib.stream()), "syrk_accum")
-        self._staged = 0
+    def _release(self):
+        acc, self._acc = self._acc, None
+        if acc is not None:
+            acc.members -= 1
+            if acc.members <= 0:
+                acc._unregister()
+
+    def _own_accumulator(self):
+        """The accumulator in the state matching this object's own history (forks away from siblings if needed)."""
+        acc = self._acc
+        if acc is None:
+            acc = self._acc = _Accumulator(self.columns, self.dev)
+            acc.count = self.nsamples
+        elif acc.members > 1 and acc.count != self.nsamples and not acc.reduced and not acc.sealed:
+            self._fork()
+            acc = self._acc
+        return acc
 
     @property
     def H(self):
         """(2/nsamples) * sum x x^T as a full symmetric fp32 matrix (what gptq.py:59-65 maintains)."""
-        if self._H is None and self._S is not None:
-            self._flush()
-            H = self._S.clone()
-            _lib.check(_lib.load().gptq_b200_symmetrize(H.data_ptr(), self.columns, self.columns, _lib.stream()),
-                       "symmetrize")
-            if self.nsamples > 0:
-                H.mul_(2.0 / self.nsamples)
-            self._H = H
+        if self._H is None and not self._consumed:
+            self._H = self._own_accumulator().materialize(self.nsamples)
         return self._H
 
     @H.setter
     def H(self, value):
         self._H = value
-        if value is None:
-            self._S = None
+        self._release()
+        self._consumed = value is None
 
     @H.deleter
     def H(self):
@@ -207,16 +441,22 @@ class GPTQ:
     @property
     def input(self):
         """gptq.py:63: mean over tokens of sqrt(2/n) * (last batch)."""
-        if self._last is None:
+        acc = self._acc
+        if acc is None or acc.last is None:
             raise AttributeError("input")
-        x, n = self._last
+        x, n = acc.last
         return math.sqrt(2 / n) * x.float().mean(0)
 
     def raw_accumulator(self):
         """Unscaled S (after folding in anything still staged) -- what multi-GPU runs all-reduce."""
-        self._flush()
+        acc = self._own_accumulator()
+        if acc.sealed:
+            raise RuntimeError("raw_accumulator: the Hessian was already finished by fasterquant")
+        if acc.S is None:
+            acc.S = torch.zeros((self.columns, self.columns), device=self.dev, dtype=torch.float32)
+        acc.flush()
         self._H = None
-        return self._S
+        return acc.S
 
     # ------------------------------------------------------------------ solve (gptq.py:126-309)
     def fasterquant(self, blocksize=128, percdamp=.01, groupsize=-1, actorder=False, static_groups=False,
@@ -246,84 +486,44 @@ class GPTQ:
             raise RuntimeError("Quantizer.configure() was not called")
 
         tick = time.time()
-        if self._H is None and self._S is not None:     # consume the accumulator in place (no clone)
-            self._flush()
-            H = self._S
-            _lib.check(lib.gptq_b200_symmetrize(H.data_ptr(), K, K, st), "symmetrize")
-            if self.nsamples > 0:
-                H.mul_(2.0 / self.nsamples)
-        else:
-            H = self._H                                 # a user-provided / already materialised H (gptq.py:141-142)
-        self._H = None
-        self._S = None
-        self._stage = None
-        self._last = None
-        if H is None:
+        if self._consumed:
             raise RuntimeError("fasterquant: H was already consumed or freed")
+        if self._H is not None:                         # a user-provided / already materialised H (gptq.py:141-142)
+            sol = _solve_hessian(self._H, K, percdamp, actorder)
+            flag = None
+        else:                                           # the accumulator, finished in place; siblings reuse the solve
+            acc = self._own_accumulator()
+            H = acc.seal(self.nsamples)
+            _dbg("seal")
+            skey = (float(percdamp), bool(actorder))
+            sol = acc.solves.get(skey)
+            if sol is None:
+                sol = acc.solves[skey] = _solve_hessian(H, K, percdamp, actorder, dead=acc.dead)
+            flag = acc.flag
+            del H, acc
+        self._H = None
+        self._consumed = True
+        dead, perm, invperm, U, info, Kp = (sol[k] for k in ("dead", "perm", "invperm", "U", "info", "Kp"))
 
         f32 = dict(device=dev, dtype=torch.float32)
-        _p0 = _prof("prologue")
-        _p0.__enter__()
-        dead = torch.empty(K, device=dev, dtype=torch.uint8)
-        diag = torch.empty(K, **f32)
-        damp = torch.empty(1, **f32)
-        ndead = torch.empty(1, device=dev, dtype=torch.int32)
-        _lib.check(lib.gptq_b200_dead_columns(H.data_ptr(), K, K, dead.data_ptr(), st), "dead_columns")
-        _lib.check(lib.gptq_b200_hessian_prepare(H.data_ptr(), K, K, float(percdamp), diag.data_ptr(), damp.data_ptr(),
-                                                 ndead.data_ptr(), st), "hessian_prepare")
-        W32 = torch.empty((R, K), **f32)
-        _lib.check(lib.gptq_b200_weights_prepare(W.data_ptr(), _lib.dt(W), R, K, W.stride(0), dead.data_ptr(),
-                                                 W32.data_ptr(), K, st), "weights_prepare")
-
-        grouped = groupsize != -1
-        ng = 1 if not grouped else (K + groupsize - 1) // groupsize
-        gscale = gzero = None
-        if static_groups and grouped:                   # gptq.py:157-163, on the un-permuted, un-updated W
-            gscale, gzero = find_params_groups(W32, maxq, q.sym, q.mse, q.norm, q.grid, q.maxshrink, groupsize)
-
-        perm = invperm = None
-        if actorder:                                    # gptq.py:165-169
-            perm = torch.empty(K, device=dev, dtype=torch.int32)
-            invperm = torch.empty(K, device=dev, dtype=torch.int32)
-            _lib.check(lib.gptq_b200_argsort_desc(diag.data_ptr(), K, perm.data_ptr(), invperm.data_ptr(), st), "argsort")
-            Wp = torch.empty_like(W32)
-            _lib.check(lib.gptq_b200_permute_cols(W32.data_ptr(), R, K, K, perm.data_ptr(), Wp.data_ptr(), K, st),
-                       "permute_cols")
-            del W32
-        else:
-            Wp = W32
-
-        Kp = _round_up(K, 128)                          # gptq.py:174-180
-        A = torch.empty((Kp, Kp), **f32)
-        _lib.check(lib.gptq_b200_hessian_gather(H.data_ptr(), K, K, _lib.ptr(perm), damp.data_ptr(), A.data_ptr(), Kp, Kp,
-                                                st), "hessian_gather")
-        del H
-        _p0.__exit__()
-        # Linears of one subset that see the same activations (q/k/v, gate/up) reach this point with bit-identical A.
-        # The chain is a pure function of A, so it is computed once per distinct A: the candidate is compared with the
-        # previous input EXACTLY (torch.equal, on device); the memo lives until the next GPTQ object is constructed
-        # (= the next calibration round), so nothing is ever reused across layers, subsets or benchmark steps.
-        hit = None
-        if CHAIN_MEMO:
-            ent = _CHAIN_MEMO.get((dev, Kp))
-            if ent is not None and torch.equal(A, ent[0]):
-                hit = ent
-        if hit is not None:
-            _, U, info = hit
-            del A
-        else:
-            A_in = A.clone() if CHAIN_MEMO else None
-            info = torch.zeros(1, device=dev, dtype=torch.int32)
-            nws = lib.gptq_b200_hinv_upper_workspace_bytes(Kp)
-            ws = torch.empty(nws, device=dev, dtype=torch.uint8)
-            U = torch.empty((Kp, Kp), **f32)
-            with _prof("hinv_upper", 2.0 / 3.0 * Kp ** 3):
-                _lib.check(lib.gptq_b200_hinv_upper(A.data_ptr(), Kp, Kp, U.data_ptr(), Kp, info.data_ptr(), ws.data_ptr(),
-                                                    nws, st), "hinv_upper")
-            del ws, A
-            if CHAIN_MEMO:
-                _CHAIN_MEMO.clear()
-                _CHAIN_MEMO[(dev, Kp)] = (A_in, U, info)
+        with _prof("prologue"):
+            W32 = torch.empty((R, K), **f32)
+            _lib.check(lib.gptq_b200_weights_prepare(W.data_ptr(), _lib.dt(W), R, K, W.stride(0), dead.data_ptr(),
+                                                     W32.data_ptr(), K, st), "weights_prepare")
+            _dbg("weights_prepare")
+            grouped = groupsize != -1
+            ng = 1 if not grouped else (K + groupsize - 1) // groupsize
+            gscale = gzero = None
+            if static_groups and grouped:               # gptq.py:157-163, on the un-permuted, un-updated W
+                gscale, gzero = find_params_groups(W32, maxq, q.sym, q.mse, q.norm, q.grid, q.maxshrink, groupsize)
+                _dbg("find_params_groups")
+            if actorder:                                # gptq.py:168
+                Wp = torch.empty_like(W32)
+                _lib.check(lib.gptq_b200_permute_cols(W32.data_ptr(), R, K, K, perm.data_ptr(), Wp.data_ptr(), K, st),
+                           "permute_cols")
+                del W32
+            else:
+                Wp = W32
 
         if not q.ready():                               # gptq.py:181-185
             q.find_params(Wp)
@@ -365,6 +565,10 @@ class GPTQ:
                                               _lib.dt(Wout), K, codes_out.data_ptr(), K, st), "finalize")
 
         torch.cuda.synchronize()                        # gptq.py:292
+        self._release()
+        if flag is not None and int(flag.item()) != 0:
+            raise RuntimeError("GPTQ: a batch assumed identical for linears sharing one Hessian accumulator differed "
+                               "(the tensor was modified between their forward hooks); set GPTQ_B200_SHARE_H=0")
         bad = int(info.item())
         if bad != 0:
             raise torch.linalg.LinAlgError(
@@ -405,9 +609,6 @@ class GPTQ:
             self.inp1 = None
             self.out1 = None
         self.H = None
-        self._stage = None
-        self._ws = None
-        self._last = None
         self.Losses = None
         self.Trace = None
         # The reference calls torch.cuda.empty_cache() here (gptq.py:318), which forces a cudaFree/cudaMalloc

@@ -61,6 +61,11 @@ int gptq_b200_symmetrize(float* H, int K, int64_t ldh, void* stream);
 /* Copy one calibration batch [tokens,K] (any ld) into a staging slab with ld_dst % 8 == 0. */
 int gptq_b200_stage_input(const void* src, int dtype, int64_t tokens, int K, int64_t ld_src,
                           void* dst, int64_t ld_dst, void* stream);
+/* *flag |= 1 if the 16-bit batches a[tokens,K] and b[tokens,K] differ in any bit (flag is NOT cleared).
+ * gptq.py:38-65 recomputes the same H for every linear that sees the same activations (q/k/v,
+ * gate/up); the host shares one accumulator between them, after this check proves the inputs equal. */
+int gptq_b200_compare_rows(const void* a, int64_t lda, const void* b, int64_t ldb, int64_t tokens, int K,
+                           int32_t* flag, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (2) fasterquant prologue.  Replaces gptq.py:130-145 (clone().float(), dead columns),

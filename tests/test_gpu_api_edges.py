@@ -186,47 +186,121 @@ def test_rtn_baseline_matches_reference_semantics():
     assert torch.equal(got.cpu(), O.quantize(W, s, z, qp.maxq))
 
 
-def test_chain_memo_is_exact_and_scoped_to_one_round():
-    """q/k/v-style linears (same activations) share one inverse-Cholesky chain; different activations never do."""
-    from gptq_b200 import _lib
-    import gptq_b200.gptq as G
-    K, R = 256, 24
+def _three_linears(K, R):
     Ws = [(torch.randn(R, K, generator=torch.Generator().manual_seed(s)) * 0.02).half() for s in range(3)]
-    X = [_acts(300, K, i) for i in range(2)]
     lins = []
     for W in Ws:
         lin = nn.Linear(K, R, bias=False).half().to(DEV)
         lin.weight.data = W.to(DEV)
         lins.append(lin)
+    return Ws, lins
+
+
+def test_linears_seeing_the_same_tensor_share_one_hessian_and_one_chain():
+    """q/k/v-style linears (their hooks receive the very same tensor) share the accumulator, the prologue and the
+    inverse-Cholesky chain; results equal the unshared run bit for bit; different activations never share."""
+    from gptq_b200 import _lib
+    import gptq_b200.gptq as G
+    K, R = 256, 24
+    Ws, lins = _three_linears(K, R)
+    X = [_acts(300, K, i).to(DEV) for i in range(3)]
     gs = [_gptq(l) for l in lins]                                   # all constructed first, like the reference drivers
+    other = _acts(300, K, 7).to(DEV)
     for x in X:
         for g in gs[:2]:
-            g.add_batch(x.to(DEV), None)                            # same tensor content -> identical H
-    gs[2].add_batch(_acts(300, K, 7).to(DEV), None)                 # different activations
+            g.add_batch(x.unsqueeze(0), None)                       # same memory, like the hooks of q/k/v
+    gs[2].add_batch(other, None)                                    # different activations
+    assert gs[0]._acc is gs[1]._acc and gs[0]._acc.members == 2
+    assert gs[2]._acc is not gs[0]._acc
+    assert gs[0].nsamples == gs[1].nsamples == 3
     st = O.HessianState(K)
     for x in X:
-        O.add_batch(st, x)
+        O.add_batch(st, x.cpu())
+    assert O.rel_fro(gs[1].H.cpu(), st.H) < 1e-5                    # reading H does not disturb the sharing
     counts = []
     for g in gs:
         n0 = _lib.launch_count()
         _quiet(g.fasterquant, groupsize=128, actorder=True)
         counts.append(_lib.launch_count() - n0)
     assert counts[1] < counts[0] and counts[2] >= counts[0] - 2     # 2nd reuses the chain, 3rd recomputes
-    for W, lin, g in zip(Ws[:2], lins[:2], gs[:2]):
+    for W, g in zip(Ws[:2], gs[:2]):
         ref = O.fasterquant(W, st.H, O.QParams(bits=4), groupsize=128, actorder=True)
         assert O.code_agreement(g.codes.cpu(), ref.codes) >= 0.999
-    # with the memo off the second linear gives bit-identical codes
-    G.CHAIN_MEMO = False
+    # with sharing off every linear accumulates and solves on its own -- and gives bit-identical results
+    G.SHARE_H = False
     try:
-        lin = nn.Linear(K, R, bias=False).half().to(DEV)
-        lin.weight.data = Ws[1].to(DEV)
-        g = _gptq(lin)
+        _, lins2 = _three_linears(K, R)
+        gs2 = [_gptq(l) for l in lins2[:2]]
         for x in X:
-            g.add_batch(x.to(DEV), None)
-        _quiet(g.fasterquant, groupsize=128, actorder=True)
-        assert torch.equal(g.codes, gs[1].codes)
+            for g in gs2:
+                g.add_batch(x.unsqueeze(0), None)
+        assert gs2[0]._acc is not gs2[1]._acc
+        for g in gs2:
+            _quiet(g.fasterquant, groupsize=128, actorder=True)
+        for a, b, la, lb in zip(gs[:2], gs2, lins[:2], lins2[:2]):
+            assert torch.equal(a.codes, b.codes)
+            assert torch.equal(la.weight.data, lb.weight.data)
+            assert a.error == b.error
     finally:
-        G.CHAIN_MEMO = True
-    assert len(G._CHAIN_MEMO) == 0 or True
-    _gptq(nn.Linear(K, R, bias=False).half().to(DEV))
-    assert len(G._CHAIN_MEMO) == 0                                   # constructing a GPTQ starts a new round
+        G.SHARE_H = True
+
+
+def test_shared_accumulator_forks_when_the_batches_diverge():
+    """Two linears share their first batches, then receive different tensors: each must end with its own exact H."""
+    K, R = 128, 8
+    _, lins = _three_linears(K, R)
+    a, b = _gptq(lins[0]), _gptq(lins[1])
+    X = [_acts(200, K, i).to(DEV) for i in range(4)]
+    Ya = _acts(200, K, 50).to(DEV)
+    Yb = _acts(200, K, 51).to(DEV)
+    for x in X[:2]:
+        a.add_batch(x, None)
+        b.add_batch(x, None)
+    assert a._acc is b._acc
+    a.add_batch(Ya, None)
+    b.add_batch(Yb, None)                                           # diverges one batch behind the leader
+    assert a._acc is not b._acc
+    a.add_batch(X[2], None)
+    b.add_batch(X[3], None)
+    for g, seq in ((a, X[:2] + [Ya, X[2]]), (b, X[:2] + [Yb, X[3]])):
+        st = O.HessianState(K)
+        for x in seq:
+            O.add_batch(st, x.cpu())
+        assert g.nsamples == 4
+        assert O.rel_fro(g.H.cpu(), st.H) < 1e-5
+
+
+def test_in_place_modification_between_sibling_hooks_is_detected():
+    """Same memory, different content: the device-side compare flags it and fasterquant refuses to continue."""
+    K, R = 128, 8
+    _, lins = _three_linears(K, R)
+    a, b = _gptq(lins[0]), _gptq(lins[1])
+    x = _acts(256, K, 3).to(DEV)
+    a.add_batch(x, None)
+    x[5, 7] += 1.0                                                  # the caller mutates the tensor between the two hooks
+    b.add_batch(x, None)
+    assert a._acc is b._acc
+    with pytest.raises(RuntimeError, match="GPTQ_B200_SHARE_H"):
+        _quiet(a.fasterquant)
+
+
+def test_sibling_can_read_H_and_free_in_any_order():
+    K, R = 128, 8
+    Ws, lins = _three_linears(K, R)
+    a, b = _gptq(lins[0]), _gptq(lins[1])
+    X = [_acts(256, K, i).to(DEV) for i in range(2)]
+    for x in X:
+        a.add_batch(x, None)
+        b.add_batch(x, None)
+    st = O.HessianState(K)
+    for x in X:
+        O.add_batch(st, x.cpu())
+    _quiet(a.fasterquant)
+    a.free()
+    assert O.rel_fro(b.H.cpu(), st.H) < 1e-5                        # b still sees the (finished) shared Hessian
+    _quiet(b.fasterquant)                                           # uses the materialised copy: private solve
+    ref = O.fasterquant(Ws[1], st.H, O.QParams(bits=4))
+    assert O.code_agreement(b.codes.cpu(), ref.codes) >= 0.999
+    with pytest.raises(RuntimeError):
+        b.add_batch(X[0], None)                                     # consumed, like `del self.H` in the reference
+    b.free()
