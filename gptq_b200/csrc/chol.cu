@@ -13,6 +13,7 @@
 // Block size 128.  Diagonal blocks are factored AND inverted by one CTA with one matrix row per
 // 8x8 register tile per thread (256 threads); everything else is fp32 GEMMs (sgemm.cu).
 #include "sgemm.cuh"
+#include "ptx.cuh"
 
 namespace gq {
 
@@ -117,6 +118,8 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
     __shared__ float rd[CB];                             // 1 / R[j][j]
     const int tid = threadIdx.x;
     const int tx = tid >> 4, ty = tid & 15;
+    ptx::pdl_launch_dependents();
+    ptx::pdl_wait();                                     // A_jj carries the preceding GEMM's Schur update
 
     float r[8][8];                                       // 64 independent loads per thread: one memory latency
 #pragma unroll
@@ -124,7 +127,7 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const int row = a * 16 + ty, col = b * 16 + tx;
-            r[a][b] = (col >= row) ? Ablk[(int64_t)row * lda + col] : 0.f;
+            r[a][b] = (col >= row) ? __ldcg(&Ablk[(int64_t)row * lda + col]) : 0.f;   // L2: written by the kernel just before (PDL)
         }
 
     chol_phase1_block<7>(r, colb, rd, info, base_index, tx, ty);
@@ -176,15 +179,18 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
 //     V12 = -S * V22
 // Every product is a square-ish fp32 GEMM with triangular-operand k-range skipping.
 struct HinvCtx {
-    float* A; int64_t lda; float* V; int64_t ldv; float* S; int32_t* info; cudaStream_t st; size_t smem; int rc;
+    float* A; int64_t lda; float* V; int64_t ldv; float* S; int32_t* info; cudaStream_t st; size_t smem; int rc; bool first;
 };
 
 static void hinv_rec(HinvCtx& c, int a, int b) {
     if (c.rc) return;
     if (b - a == 1) {
         const int c0 = a * CB;
-        chol_diag_kernel<<<1, 256, c.smem, c.st>>>(c.A + (int64_t)c0 * c.lda + c0, c.lda, c.V + (int64_t)c0 * c.ldv + c0,
-                                                   c.ldv, c.info, c0);
+        const bool pdl_ok = !c.first;      // the very first kernel follows the memsets of info / U
+        c.first = false;
+        cudaError_t e = launch_pdl(pdl_ok, chol_diag_kernel, dim3(1), dim3(256), c.smem, c.st, c.A + (int64_t)c0 * c.lda + c0, c.lda,
+                                   c.V + (int64_t)c0 * c.ldv + c0, c.ldv, c.info, c0);
+        if (e != cudaSuccess) { c.rc = set_err((int)e, "hinv_upper: diagonal-block launch failed: %s", cudaGetErrorString(e)); return; }
         g_launches.fetch_add(1, std::memory_order_relaxed);
         return;
     }
@@ -243,7 +249,7 @@ extern "C" int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, float* U, int
     }
     GQ_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     GQ_CUDA(cudaMemset2DAsync(U, ldu * sizeof(float), 0, (size_t)Kp * sizeof(float), Kp, st));
-    HinvCtx c{A, lda, U, ldu, static_cast<float*>(ws), info, st, smem, 0};
+    HinvCtx c{A, lda, U, ldu, static_cast<float*>(ws), info, st, smem, 0, true};
     hinv_rec(c, 0, Kp / CB);
     if (c.rc) return c.rc;
     cudaError_t e = cudaGetLastError();

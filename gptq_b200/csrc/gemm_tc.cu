@@ -25,6 +25,9 @@
 
 namespace gq {
 
+extern int g_gemm_splitk;
+extern int g_gemm_splitk_minkb;
+
 constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 32;
 constexpr int GT_STAGES = 2;
 constexpr int GT_A_BYTES = GT_BM * GT_BK * 4;        // 16 KB
@@ -34,8 +37,12 @@ constexpr int GT_THREADS = 320;
 constexpr int GT_CHUNK = 1;                           // k-blocks per TMEM accumulation chain (12 MMAs)
 constexpr int GT_SMEM = GT_STAGES * GT_STAGE_BYTES + 1024 + 256;
 
+constexpr int GT_TP = GT_BM + 4;                      // pitch of the transposed partial tile in shared memory (split-K):
+                                                      // 16-byte aligned columns, conflict-free for float4 reads along the columns
+
 struct GemmTcParams {
     int M, N, Kd; float alpha, beta; float* C; int64_t ldc; int mode; int a_mn, b_mn; uint32_t idesc;
+    int splits;                                       // cluster size along z: the k-range of a tile is split over the cluster
 };
 
 __device__ __forceinline__ float rn_tf32(float x) {
@@ -52,7 +59,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int kbeg = 0, kend = p.Kd;
     if (p.mode & SG_A_UPPER) kbeg = (m0 / GT_BK) * GT_BK;
     if (p.mode & SG_B_UPPER) kend = min(p.Kd, n0 + GT_BN);
-    const int nkb = kend > kbeg ? (kend - kbeg + GT_BK - 1) / GT_BK : 0;
+    int nkb = kend > kbeg ? (kend - kbeg + GT_BK - 1) / GT_BK : 0;
+    // split-K: the CTAs of a cluster (same tile, z = rank) take consecutive slices of the k-blocks and reduce their
+    // partial tiles through distributed shared memory in rank order (deterministic, no atomics, no workspace)
+    const int S = p.splits;
+    const int zr = S > 1 ? (int)ptx::cluster_ctarank() : 0;
+    if (S > 1) {
+        const int per = (nkb + S - 1) / S;
+        const int kb0 = zr * per;
+        kbeg += kb0 * GT_BK;
+        nkb = max(0, min(per, nkb - kb0));
+    }
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -78,6 +95,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    ptx::pdl_launch_dependents();      // the next kernel may start its prologue; it waits for our completion itself
+    ptx::pdl_wait();                   // operands (and C when beta != 0) come from the preceding kernels of the stream
 
     if (warp == 0) {
         if (lane == 0) {
@@ -204,7 +223,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
         const int row = m0 + quad * 32 + lane;
         const int col0 = n0 + half * 128;
-        if (row < p.M) {
+        if (S > 1) {
+            // partial tile -> own shared memory, transposed [col][row] (pitch 129: conflict-free both ways); every MMA
+            // that read the stage buffers has retired (final drain) and no TMA is in flight
+            float* T = reinterpret_cast<float*>(smem);
+            const int r = quad * 32 + lane;
+#pragma unroll
+            for (int q = 0; q < 128; ++q) T[(half * 128 + q) * GT_TP + r] = acc[q];
+        } else if (row < p.M) {
             float* dst = p.C + (int64_t)row * p.ldc + col0;
             const int cols_ok = min(128, p.N - col0);
             const bool vec = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0);
@@ -217,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int q = 0; q < 8; ++q) {
                         float4 r;
                         if (p.beta != 0.f) {
-                            const float4 c = *reinterpret_cast<const float4*>(o + q * 4);
+                            const float4 c = __ldcg(reinterpret_cast<const float4*>(o + q * 4));
                             r.x = fmaf(p.alpha, acc[cb * 32 + q * 4 + 0], p.beta * c.x); r.y = fmaf(p.alpha, acc[cb * 32 + q * 4 + 1], p.beta * c.y);
                             r.z = fmaf(p.alpha, acc[cb * 32 + q * 4 + 2], p.beta * c.z); r.w = fmaf(p.alpha, acc[cb * 32 + q * 4 + 3], p.beta * c.w);
                         } else {
@@ -229,10 +255,51 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else if (nc > 0) {
 #pragma unroll
                     for (int q = 0; q < 32; ++q)
-                        if (q < nc) o[q] = (p.beta != 0.f) ? fmaf(p.alpha, acc[cb * 32 + q], p.beta * o[q]) : p.alpha * acc[cb * 32 + q];
+                        if (q < nc) o[q] = (p.beta != 0.f) ? fmaf(p.alpha, acc[cb * 32 + q], p.beta * __ldcg(o + q)) : p.alpha * acc[cb * 32 + q];
                 }
             }
         }
+    }
+
+    if (S > 1) {
+        __syncwarp();
+        ptx::cluster_sync();                                   // all partial tiles written
+        if (warp >= 2) {
+            // rank zr owns columns [zr*W, (zr+1)*W) of the tile: sum the S partials in rank order, apply alpha/beta.
+            // item = (32-column group, 4-row group); lane <-> column, so the global accesses are 128-byte rows and the
+            // DSMEM reads are one float4 (4 consecutive rows of one column) per rank, all issued before the sums.
+            const int W = GT_BN / S;
+            const uint32_t tbase = ptx::smem_u32(smem);
+            const int ew = warp - 2;
+            const int n_items = W;                              // (W/32) column groups x 32 row groups
+            for (int it = ew; it < n_items; it += 8) {
+                const int cg = it >> 5, rq = it & 31;
+                const int col = zr * W + cg * 32 + lane;
+                const uint32_t off = (uint32_t)(col * GT_TP + rq * 4) * 4u;
+                float4 v[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    if (c < S) v[c] = ptx::ld_dsmem_f32x4(ptx::mapa(tbase, (uint32_t)c) + off);
+                float4 s = v[0];
+#pragma unroll
+                for (int c = 1; c < 8; ++c)
+                    if (c < S) { s.x = __fadd_rn(s.x, v[c].x); s.y = __fadd_rn(s.y, v[c].y); s.z = __fadd_rn(s.z, v[c].z); s.w = __fadd_rn(s.w, v[c].w); }
+                const float sv[4] = {s.x, s.y, s.z, s.w};
+                const int gc = n0 + col;
+                if (gc < p.N) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int gr = m0 + rq * 4 + q;
+                        if (gr < p.M) {
+                            float* o = p.C + (int64_t)gr * p.ldc + gc;
+                            *o = (p.beta != 0.f) ? fmaf(p.alpha, sv[q], p.beta * __ldcg(o)) : p.alpha * sv[q];
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        ptx::cluster_sync();                                   // nobody leaves while a peer still reads its tile
     }
 
     ptx::tc_fence_before();
@@ -300,8 +367,39 @@ int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, co
     p.M = M; p.N = N; p.Kd = Kd; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.mode = mode;
     p.a_mn = transa ? 1 : 0; p.b_mn = transb ? 0 : 1;
     p.idesc = ptx::make_idesc(2, p.a_mn, p.b_mn, GT_BM, GT_BN);
-    dim3 grid(cdiv(N, GT_BN), cdiv(M, GT_BM));
-    gemm_tc_kernel<<<grid, GT_THREADS, GT_SMEM, st>>>(tmA, tmB, p);
+    const int gx = cdiv(N, GT_BN), gy = cdiv(M, GT_BM);
+    // split-K over a thread-block cluster when the tiles alone cannot fill the GPU (the chain's lower levels, the
+    // narrow lazy updates): largest power of two with >= 2 k-blocks per CTA and at most one CTA per SM
+    int tiles = gx * gy;
+    if (mode & SG_UPPER_TILES) {
+        tiles = 0;
+        for (int y = 0; y < gy; ++y)
+            for (int x = 0; x < gx; ++x) tiles += (x * GT_BN + GT_BN - 1 >= y * GT_BM) ? 1 : 0;
+    }
+    const int nkb = cdiv(Kd, GT_BK);
+    int S = 1;
+    if (g_gemm_splitk)
+        while (S * 2 <= 8 && tiles * S * 2 <= num_sms() && nkb / (S * 2) >= g_gemm_splitk_minkb) S *= 2;
+    p.splits = S;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(gx, gy, S);
+    cfg.blockDim = dim3(GT_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = GT_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (S > 1) {
+        at[na].id = cudaLaunchAttributeClusterDimension;
+        at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = S;
+        ++na;
+    }
+    if (g_pdl && !(mode & SG_NO_PDL)) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    GQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, tmA, tmB, p));
     GQ_LAUNCHED();
     return 0;
 }
@@ -312,6 +410,17 @@ static int backend_from_env() {
     return 1;
 }
 int g_gemm_backend = backend_from_env();
+static int flag_from_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? (e[0] != '0') : dflt;
+}
+int g_gemm_splitk = flag_from_env("GPTQ_B200_SPLITK", 1);
+static int int_from_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+int g_gemm_splitk_minkb = int_from_env("GPTQ_B200_SPLITK_MINKB", 4);   // fewest k-blocks (of 32) a split may get
+int g_pdl = flag_from_env("GPTQ_B200_PDL", 1);
 
 int gemm_fp32(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda, const float* B,
               int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st) {
@@ -339,5 +448,5 @@ extern "C" int gptq_b200_gemm3x(int transa, int transb, int M, int N, int Kd, fl
     GQ_ARG(ldb >= (transb ? Kd : N) && ldb % 4 == 0, 10, "ldb too small or not a multiple of 4");
     GQ_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0, 7, "A/B must be 16-byte aligned");
     GQ_ARG(ldc >= N, 13, "ldc<N");
-    return gemm_tc_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, SG_FULL, as_stream(stream));
+    return gemm_tc_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, SG_FULL | SG_NO_PDL, as_stream(stream));
 }

@@ -62,6 +62,7 @@ argsort_desc_kernel(const float* __restrict__ v, int n, int32_t* __restrict__ pe
     __shared__ float tile[1024];
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     float vi = (i < n) ? v[i] : 0.f;
+    const bool ni = vi != vi;
     int rank = 0;
     for (int base = 0; base < n; base += 1024) {
         int m = min(1024, n - base);
@@ -72,7 +73,9 @@ argsort_desc_kernel(const float* __restrict__ v, int n, int32_t* __restrict__ pe
             for (int t = 0; t < m; ++t) {
                 float vj = tile[t];
                 int j = base + t;
-                rank += (vj > vi) || (vj == vi && j < i);
+                // total order (NaN first, like torch.argsort descending) so perm is a permutation for ANY input
+                const bool nj = vj != vj;
+                rank += ni ? (nj && j < i) : (nj || (vj > vi) || (vj == vi && j < i));
             }
         }
     }

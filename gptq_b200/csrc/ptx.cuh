@@ -101,6 +101,36 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ thread-block clusters / distributed shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// All threads of all CTAs of the cluster; release/acquire makes prior shared-memory writes visible cluster-wide.
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta_rank));
+    return r;
+}
+// Not volatile / no memory clobber on purpose: independent loads must be free to overlap; ordering against the
+// producers is provided by cluster_sync() (which is a compiler barrier) before and after the reads.
+__device__ __forceinline__ float4 ld_dsmem_f32x4(uint32_t cluster_addr) {
+    float4 v;
+    asm("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr));
+    return v;
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// wait: blocks until the preceding kernel of the stream has completed and its writes are visible (no-op when the
+// kernel was not launched with programmatic stream serialization).  launch: lets the next kernel's CTAs start
+// their prologue on free SMs while this grid is still running.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ descriptors (cute/arch/mma_sm100_desc.hpp bit layout)
 // Shared-memory matrix descriptor, SWIZZLE_128B, version 1 (sm_100).
 //   MN-major operand: LBO = byte stride between 64-element MN atoms, SBO = byte stride between 8-row K atoms.

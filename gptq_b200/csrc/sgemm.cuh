@@ -9,6 +9,7 @@ enum SgemmMode {          // bit mask
     SG_UPPER_TILES = 1,   // C square: skip tiles that lie strictly below the diagonal
     SG_A_UPPER = 2,       // op(A) is upper triangular (op(A)[m][k] == 0 for k < m): skip leading k
     SG_B_UPPER = 4,       // op(B) is upper triangular (op(B)[k][n] == 0 for k > n): skip trailing k
+    SG_NO_PDL = 8,        // the preceding stream operation is not one of our kernels: launch fully serialized
 };
 
 // C[M,N] <- alpha * op(A) op(B) + beta * C   (row-major, fp32, IEEE FMA accumulation)

@@ -304,3 +304,20 @@ def test_sibling_can_read_H_and_free_in_any_order():
     with pytest.raises(RuntimeError):
         b.add_batch(X[0], None)                                     # consumed, like `del self.H` in the reference
     b.free()
+
+
+def test_non_finite_activations_raise_linalgerror_instead_of_faulting():
+    """A NaN in the calibration data poisons diag(H): the act-order argsort must still emit a permutation and the
+    chain must report non-PD (torch.linalg.cholesky raises LinAlgError for the reference too, gptq.py:177)."""
+    K, R = 256, 16
+    lin = nn.Linear(K, R, bias=False).half().to(DEV)
+    x = _acts(300, K, 0)
+    x[3, 5] = float("nan")
+    g = _gptq(lin)
+    g.add_batch(x.to(DEV), None)
+    with pytest.raises(torch.linalg.LinAlgError):
+        _quiet(g.fasterquant, actorder=True, groupsize=128)
+    torch.cuda.synchronize()                                          # the context is still healthy
+    g2 = _gptq(nn.Linear(K, R, bias=False).half().to(DEV))
+    g2.add_batch(_acts(300, K, 1).to(DEV), None)
+    _quiet(g2.fasterquant, actorder=True, groupsize=128)
