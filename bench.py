@@ -206,6 +206,38 @@ def _copy_stream(dev):
     return _COPY_STREAMS[dev]
 
 
+_H2D = {}
+
+
+def _h2d_buffers(dev, nbytes):
+    """Two device landing buffers (one per in-flight subset) and their 'consumed' events, allocated once."""
+    st = _H2D.get(dev)
+    if st is None or st["bufs"][0].numel() < nbytes:
+        st = {"bufs": [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
+              "consumed": [None, None]}
+        _H2D[dev] = st
+    return st
+
+
+def _enqueue_subset_h2d(dev, X, slot):
+    """Caller side of the public API when the activations live in pinned host memory: stream the samples of one
+    subset into landing buffer `slot` on the copy stream, one event per sample.  Returns (device view, events)."""
+    cs = _copy_stream(dev)
+    st = _h2d_buffers(dev, NSAMPLES * SEQ * max(ACT_K) * 2)
+    n = X.numel() * X.element_size()
+    view = st["bufs"][slot][:n].view(X.dtype).view(X.shape)
+    ready = []
+    with torch.cuda.stream(cs):
+        if st["consumed"][slot] is not None:
+            cs.wait_event(st["consumed"][slot])           # the previous occupant of this buffer has been staged
+        for j in range(X.shape[0]):
+            view[j].copy_(X[j], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+            ready.append(ev)
+    return view, ready
+
+
 def quantize_layer(dev, acts, weights, world, from_host):
     """One step: the reference driver's per-layer flow (llama.py:97-170) over our GPTQ / Quantizer / pack."""
     import torch.nn as nn
@@ -214,7 +246,13 @@ def quantize_layer(dev, acts, weights, world, from_host):
     from gptq_b200 import dist as gd
     results = []
     d2h = 0
-    for subset in SUBSETS:
+    cur = torch.cuda.current_stream()
+    pending = None
+    if from_host:
+        # landing buffers belong to the main stream's allocator pool: order the copy stream after everything queued
+        _copy_stream(dev).wait_stream(cur)
+        pending = _enqueue_subset_h2d(dev, acts[LINEARS[SUBSETS[0][0]][3]], 0)
+    for si, subset in enumerate(SUBSETS):
         gs = []
         for li in subset:
             name, r, c, a = LINEARS[li]
@@ -228,34 +266,21 @@ def quantize_layer(dev, acts, weights, world, from_host):
             gs.append(g)
         X = acts[LINEARS[subset[0]][3]]
         if from_host:
-            # the caller's side of the public API: samples arrive from pinned host memory; a copy stream
-            # prefetches sample j+1 into a second device buffer while sample j is being staged
-            cs = _copy_stream(dev)
-            cur = torch.cuda.current_stream()
-            bufs = [torch.empty(X.shape[1:], dtype=X.dtype, device=dev) for _ in range(2)]
-            ready = [torch.cuda.Event(), torch.cuda.Event()]
-            freed = [torch.cuda.Event(), torch.cuda.Event()]
-            # the buffers come from the main stream's allocator pool: the copy stream may only touch them after
-            # everything already queued on the main stream (previous users of that memory) has run
-            cs.wait_stream(cur)
-            with torch.cuda.stream(cs):
-                bufs[0].copy_(X[0], non_blocking=True)
-                ready[0].record(cs)
-            for j in range(X.shape[0]):
-                b = j & 1
-                if j + 1 < X.shape[0]:
-                    nb = (j + 1) & 1
-                    with torch.cuda.stream(cs):
-                        if j >= 1:
-                            cs.wait_event(freed[nb])
-                        bufs[nb].copy_(X[j + 1], non_blocking=True)
-                        ready[nb].record(cs)
-                cur.wait_event(ready[b])
-                xj = bufs[b].unsqueeze(0)
+            # the H2D stream runs one subset ahead of the compute stream (while this subset's Hessians, chain and
+            # column loops run, the next subset's samples are already landing in the other buffer)
+            Xd, ready = pending
+            if si + 1 < len(SUBSETS):
+                pending = _enqueue_subset_h2d(dev, acts[LINEARS[SUBSETS[si + 1][0]][3]], (si + 1) & 1)
+            for j in range(Xd.shape[0]):
+                cur.wait_event(ready[j])
+                xj = Xd[j].unsqueeze(0)
                 for g in gs:
                     g.add_batch(xj, None)
-                freed[b].record(cur)
-            cur.wait_stream(cs)
+            for g in gs:
+                g.raw_accumulator()                      # fold what is still staged, so the landing buffer is free
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            _H2D[dev]["consumed"][si & 1] = ev
         else:
             for j in range(X.shape[0]):
                 xj = X[j].unsqueeze(0)
@@ -264,8 +289,7 @@ def quantize_layer(dev, acts, weights, world, from_host):
         if os.environ.get("GPTQ_B200_DEBUG_SYNC"):
             torch.cuda.synchronize()
             fin = [bool(torch.isfinite(g.raw_accumulator()).all()) for g in gs]
-            print("debug: add_batch phase ok", [LINEARS[li][0] for li in subset], "S finite:", fin,
-                  "X finite:", bool(torch.isfinite(X.float()).all()) if from_host else "-", file=sys.stderr)
+            print("debug: add_batch phase ok", [LINEARS[li][0] for li in subset], "S finite:", fin, file=sys.stderr)
         for g in gs:
             if world > 1:
                 gd.allreduce_hessian(g)
@@ -278,6 +302,8 @@ def quantize_layer(dev, acts, weights, world, from_host):
                 d2h += sum(o.numel() * o.element_size() for o in outs)
             results.append((qw, g.error))
             g.free()
+    if from_host:
+        cur.wait_stream(_copy_stream(dev))
     return results, d2h
 
 

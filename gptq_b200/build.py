@@ -18,6 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 # per-file extra flags
+EXTRA_ENV = os.environ.get("GPTQ_B200_NVCC_EXTRA", "").split()
 EXTRA = {
     "colloop.cu": ["--fmad=false"],      # error feedback must not be contracted (see colloop.cu)
     "find_params.cu": ["--fmad=false"],
@@ -48,7 +49,7 @@ def compile_one(src, force=False):
     path = os.path.join(CSRC, src)
     if not force and not _stale(obj, [path] + _headers()):
         return obj, ""
-    cmd = [NVCC, *ARCH, *COMMON, *EXTRA.get(src, []), "-c", path, "-o", obj]
+    cmd = [NVCC, *ARCH, *COMMON, *EXTRA.get(src, []), *EXTRA_ENV, "-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")

@@ -23,6 +23,7 @@
 // Compiled with --fmad=false: no a*b+c in this file is contracted; every FMA below is an explicit fmaf.
 #include "sgemm.cuh"
 #include "ptx.cuh"
+#include <stdlib.h>
 
 namespace gq {
 
@@ -47,8 +48,15 @@ __device__ __forceinline__ float div_by_recip(float a, float b, float y) {
     return q;
 }
 
+// LPR = lanes per row: 4 (32 columns per lane) or 8 (16 columns per lane).  With few rows per SM (R <= ~40 x #SMs) the
+// 8-lane form doubles the warps per scheduler, which is what a latency-bound recurrence needs; with many rows the
+// 4-lane form has less redundant quantizer arithmetic per column.
+template <int LPR>
 __global__ void __launch_bounds__(BQ_MAX_ROWS * 4, 1)
 blockquant_kernel(BQArgs a) {
+    constexpr int NW = BQ_B / LPR;           // W1 columns held per lane
+    constexpr int NCH = NW / 4;              // chunks of 4 consecutive columns per lane
+    constexpr int CW = LPR * 4;              // columns covered by one chunk across the lanes of a row
     extern __shared__ __align__(16) float sm[];
     const int RPC = a.rows_per_cta;
     float* Hs = sm;                          // [128][128]
@@ -59,7 +67,7 @@ blockquant_kernel(BQArgs a) {
     __shared__ double s_loss[BQ_MAX_ROWS * 4 / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
-    const int l4 = lane & 3, rl = tid >> 2;
+    const int l4 = lane & (LPR - 1), rl = tid / LPR;
     const int row = blockIdx.x * RPC + rl;
     const bool rvalid = row < a.R;
     const int count = a.count, i1 = a.i1;
@@ -97,26 +105,43 @@ blockquant_kernel(BQArgs a) {
         s_g[i] = (a.gidx && i < count) ? a.gidx[i1 + i] : 0;
     }
     __syncthreads();
-    // ---- stage the quantizer of every (row, column) of the block (group index from smem: one level of loads)
+    // ---- stage the quantizer of every (row, column) of the block (group index from smem: one level of loads).
+    // Loads are issued in batches of 16 before anything consumes them (the reciprocal's slow path is a branch the
+    // compiler will not hoist loads across: unbatched, every entry paid a full L2 round trip -- 35 % of the kernel).
+    // scale / zero / gidx do not change while PDL-launched blocks are in flight (mode 0), so L1-cached loads are safe.
     const int row0 = blockIdx.x * RPC;
-#pragma unroll 8
-    for (int idx = tid; idx < RPC * BQ_B; idx += nthreads) {
-        const int r = idx >> 7, c = idx & 127;
-        int gr = row0 + r;
-        if (gr >= a.R) gr = a.R - 1;                         // clamp: harmless duplicate of the last row
-        const int64_t o = (int64_t)gr * a.ng + s_g[c];
-        const float s = __ldcg(&a.scale[o]), z = __ldcg(&a.zero[o]);
-        Ss[r * BQ_SP + c] = s;
-        Zs[r * BQ_SP + c] = z;
-        Ys[r * BQ_SP + c] = __frcp_rn(s);
+    for (int base = 0; base < RPC * BQ_B; base += nthreads * 16) {
+        float sv[16], zv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = base + u * nthreads + tid;
+            sv[u] = 1.f; zv[u] = 0.f;
+            if (idx < RPC * BQ_B) {
+                const int r = idx >> 7, c = idx & 127;
+                int gr = row0 + r;
+                if (gr >= a.R) gr = a.R - 1;                     // clamp: harmless duplicate of the last row
+                const int64_t o = (int64_t)gr * a.ng + s_g[c];
+                sv[u] = a.scale[o]; zv[u] = a.zero[o];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int idx = base + u * nthreads + tid;
+            if (idx < RPC * BQ_B) {
+                const int r = idx >> 7, c = idx & 127;
+                Ss[r * BQ_SP + c] = sv[u];
+                Zs[r * BQ_SP + c] = zv[u];
+                Ys[r * BQ_SP + c] = __frcp_rn(sv[u]);
+            }
+        }
     }
-    // ---- W1 slice -> registers: w[kk*4+v] = W[row][i1 + kk*16 + l4*4 + v]
-    float w[32];
-    uint32_t cpk[8];
+    // ---- W1 slice -> registers: w[kk*4+v] = W[row][i1 + kk*CW + l4*4 + v]
+    float w[NW];
+    uint32_t cpk[NCH];
     const bool wvec = ((a.ldw & 3) == 0) && ((i1 & 3) == 0) && ((((uintptr_t)a.W) & 15) == 0);
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
-        int c = kk * 16 + l4 * 4;
+    for (int kk = 0; kk < NCH; ++kk) {
+        int c = kk * CW + l4 * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (rvalid) {
             const float* p = a.W + (int64_t)row * a.ldw + i1 + c;
@@ -137,15 +162,15 @@ blockquant_kernel(BQArgs a) {
     const float* srow = Ss + rl * BQ_SP;
     const float* zrow = Zs + rl * BQ_SP;
     const float* yrow = Ys + rl * BQ_SP;
-    const int lbase = lane & ~3;
+    const int lbase = lane & ~(LPR - 1);
 
 #pragma unroll
-    for (int kk = 0; kk < 8; ++kk) {
+    for (int kk = 0; kk < NCH; ++kk) {
 #pragma unroll 1
-        for (int l = 0; l < 4; ++l) {
+        for (int l = 0; l < LPR; ++l) {
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
-                const int i = kk * 16 + l * 4 + v;
+                const int i = kk * CW + l * 4 + v;
                 if (i < count) {                                         // block-uniform
                     const float wi = __shfl_sync(0xffffffffu, w[kk * 4 + v], lbase | l);
                     const float d = Hs[i * BQ_B + i], rd = s_rd[i];
@@ -162,8 +187,8 @@ blockquant_kernel(BQArgs a) {
                     loss = fmaf(err, err, loss);                           // gptq.py:267: (w-q)^2/d^2 (reported scalar)
                     // rank-1 update of the columns this lane still owns (gptq.py:270)
 #pragma unroll
-                    for (int k2 = kk; k2 < 8; ++k2) {
-                        const float4 h = *reinterpret_cast<const float4*>(&Hs[i * BQ_B + k2 * 16 + l4 * 4]);
+                    for (int k2 = kk; k2 < NCH; ++k2) {
+                        const float4 h = *reinterpret_cast<const float4*>(&Hs[i * BQ_B + k2 * CW + l4 * 4]);
                         const float hv[4] = {h.x, h.y, h.z, h.w};
 #pragma unroll
                         for (int v2 = 0; v2 < 4; ++v2) {
@@ -186,8 +211,8 @@ blockquant_kernel(BQArgs a) {
         const bool cvec = ((a.ldc & 3) == 0) && ((i1 & 3) == 0) && ((((uintptr_t)a.codes) & 3) == 0);
         const bool evec = ((a.lde & 3) == 0) && ((((uintptr_t)a.Err) & 15) == 0);
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-            const int c = kk * 16 + l4 * 4;
+        for (int kk = 0; kk < NCH; ++kk) {
+            const int c = kk * CW + l4 * 4;
             if (c >= count) continue;
             float qv[4];
 #pragma unroll
@@ -225,6 +250,12 @@ blockquant_kernel(BQArgs a) {
         atomicAdd(a.loss, t * 0.5);                                      // Losses1 / 2, gptq.py:274
     }
 }
+
+static int bq_lpr8_from_env() {
+    const char* e = getenv("GPTQ_B200_BQ_LPR8_MAX_ROWS");
+    return e ? atoi(e) : 40;
+}
+static int g_bq_lpr8_max_rows = bq_lpr8_from_env();      // rows per CTA up to which the 8-lanes-per-row kernel is used (<= 48)
 
 // Counts (a,b) pairs for which div_by_recip(a, b, RN(1/b)) differs from div.rn.f32(a, b).
 __global__ void selftest_div_kernel(uint64_t n, uint32_t seed, int mode, unsigned long long* mismatches) {
@@ -283,9 +314,11 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
     static bool attr_done = false;
     if (!attr_done) {
         const size_t smem_max = (size_t)(BQ_B * BQ_B + 3 * BQ_MAX_ROWS * BQ_SP) * sizeof(float);
-        GQ_CUDA(cudaFuncSetAttribute(blockquant_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        GQ_CUDA(cudaFuncSetAttribute(blockquant_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+        GQ_CUDA(cudaFuncSetAttribute(blockquant_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         attr_done = true;
     }
+    const int lpr = (rpc <= g_bq_lpr8_max_rows) ? 8 : 4;
     GQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
     // Two-level lazy update (same arithmetic as gptq.py:276, regrouped): after every block only the rest of the current
     // super-block is brought up to date (narrow GEMM, depth `count`); the columns beyond it receive ONE deep GEMM per
@@ -311,7 +344,8 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
         float* Eblk = Err + (i1 - sb_start);
         BQArgs a{W, R, K, ldw, U, ldu, i1, count, gidx, scale, zero, ngroups, (float)maxq, maxq < 0 ? 1 : 0,
                  Q, ldq, codes, ldc, Eblk, lde, loss, rpc};
-        GQ_CUDA(launch_pdl(/*allow=*/i1 > 0 && mode == 0, blockquant_kernel, dim3(cdiv(R, rpc)), dim3(rpc * 4), smem, st, a));
+        if (lpr == 8) GQ_CUDA(launch_pdl(/*allow=*/i1 > 0 && mode == 0, blockquant_kernel<8>, dim3(cdiv(R, rpc)), dim3(rpc * 8), smem, st, a));
+        else GQ_CUDA(launch_pdl(/*allow=*/i1 > 0 && mode == 0, blockquant_kernel<4>, dim3(cdiv(R, rpc)), dim3(rpc * 4), smem, st, a));
         GQ_LAUNCHED();
         if (i2 < sb_end) {            // near: the rest of this super-block
             int rc = gemm_fp32(0, 0, R, sb_end - i2, count, -1.f, Eblk, lde, U + (int64_t)i1 * ldu + i2, ldu, 1.f,

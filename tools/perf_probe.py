@@ -134,9 +134,14 @@ if __name__ == "__main__":
         probe_sgemm(4096, 4096, 128)
         probe_sgemm(128, 128, 128)
         probe_sgemm(512, 512, 512)
+    if "diag" in what:
+        probe_hinv(128)
+        probe_hinv(256)
     if "hinv" in what:
         for K in (1024, 4096):
             probe_hinv(K)
+    if "hinvbig" in what:
+        probe_hinv(11008)
     if "colloop" in what:
         probe_colloop(4096, 4096)
         probe_colloop(11008, 4096)
