@@ -209,36 +209,53 @@ def _copy_stream(dev):
 _H2D = {}
 
 
-def _h2d_buffers(dev, nbytes):
-    """Two device landing buffers (one per in-flight subset) and their 'consumed' events, allocated once."""
+def _h2d_buffers(dev, nbytes, wbytes):
+    """Two device landing areas (one per in-flight subset: activations + that subset's weights) and their 'consumed'
+    events, allocated once."""
     st = _H2D.get(dev)
-    if st is None or st["bufs"][0].numel() < nbytes:
+    if st is None or st["bufs"][0].numel() < nbytes or st["wbufs"][0].numel() < wbytes:
         st = {"bufs": [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
+              "wbufs": [torch.empty(wbytes, dtype=torch.uint8, device=dev) for _ in range(2)],
               "consumed": [None, None]}
         _H2D[dev] = st
+        # fresh blocks of the compute stream's allocator pool: the copy stream may only touch them after everything
+        # already queued on the compute stream (possible previous users of that memory) has run
+        _copy_stream(dev).wait_stream(torch.cuda.current_stream())
     return st
 
 
-def _enqueue_subset_h2d(dev, X, slot):
-    """Caller side of the public API when the activations live in pinned host memory: stream the samples of one
-    subset into landing buffer `slot` on the copy stream, one event per sample.  Returns (device view, events)."""
+def _enqueue_subset_h2d(dev, X, wlist, slot):
+    """Caller side of the public API when activations and weights live in pinned host memory: stream the samples of
+    one subset, then its weights, into landing area `slot` on the copy stream (one event per sample, one for the
+    weights).  Everything host-to-device goes through this one stream: a copy issued on the compute stream would
+    queue behind the transfers already in flight and stall the kernels behind it."""
     cs = _copy_stream(dev)
-    st = _h2d_buffers(dev, NSAMPLES * SEQ * max(ACT_K) * 2)
+    wmax = max(sum(LINEARS[li][1] * LINEARS[li][2] for li in sub) for sub in SUBSETS) * 2
+    st = _h2d_buffers(dev, NSAMPLES * SEQ * max(ACT_K) * 2, wmax)
     n = X.numel() * X.element_size()
     view = st["bufs"][slot][:n].view(X.dtype).view(X.shape)
-    ready = []
+    ready, wdev = [], []
     with torch.cuda.stream(cs):
         if st["consumed"][slot] is not None:
-            cs.wait_event(st["consumed"][slot])           # the previous occupant of this buffer has been staged
+            cs.wait_event(st["consumed"][slot])           # the previous occupant of this area is done with it
         for j in range(X.shape[0]):
             view[j].copy_(X[j], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
             ready.append(ev)
-    return view, ready
+        off = 0
+        for w in wlist:
+            nb = w.numel() * w.element_size()
+            wd = st["wbufs"][slot][off:off + nb].view(w.dtype).view(w.shape)
+            wd.copy_(w, non_blocking=True)
+            wdev.append(wd)
+            off += (nb + 255) // 256 * 256
+        wev = torch.cuda.Event()
+        wev.record(cs)
+    return view, ready, wdev, wev
 
 
-def quantize_layer(dev, acts, weights, world, from_host):
+def quantize_layer(dev, acts, weights, world, from_host, carry=None, prefetch_next=False):
     """One step: the reference driver's per-layer flow (llama.py:97-170) over our GPTQ / Quantizer / pack."""
     import torch.nn as nn
     from gptq_b200.gptq import GPTQ
@@ -248,10 +265,18 @@ def quantize_layer(dev, acts, weights, world, from_host):
     d2h = 0
     cur = torch.cuda.current_stream()
     pending = None
+    trace = [] if (from_host and os.environ.get("GPTQ_B200_E2E_TRACE")) else None
+
+    def mark(name, stream):
+        if trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            trace.append((name, ev))
+    mark("step start", cur)
     if from_host:
-        # landing buffers belong to the main stream's allocator pool: order the copy stream after everything queued
-        _copy_stream(dev).wait_stream(cur)
-        pending = _enqueue_subset_h2d(dev, acts[LINEARS[SUBSETS[0][0]][3]], 0)
+        # `carry`: the previous step already queued this step's first subset behind its own last transfer
+        pending = carry if carry is not None else _enqueue_subset_h2d(
+            dev, acts[LINEARS[SUBSETS[0][0]][3]], [weights[li] for li in SUBSETS[0]], 0)
     for si, subset in enumerate(SUBSETS):
         gs = []
         for li in subset:
@@ -259,7 +284,8 @@ def quantize_layer(dev, acts, weights, world, from_host):
             lin = nn.Linear(c, r, bias=False, device="meta")
             lin.to_empty(device=dev)
             lin = lin.half()
-            lin.weight.data = weights[li].to(dev, non_blocking=True) if from_host else weights[li].clone()
+            if not from_host:
+                lin.weight.data = weights[li].clone()
             g = GPTQ(lin)
             g.quantizer = Quantizer()
             g.quantizer.configure(WBITS, perchannel=True, sym=False, mse=False)
@@ -268,19 +294,24 @@ def quantize_layer(dev, acts, weights, world, from_host):
         if from_host:
             # the H2D stream runs one subset ahead of the compute stream (while this subset's Hessians, chain and
             # column loops run, the next subset's samples are already landing in the other buffer)
-            Xd, ready = pending
-            if si + 1 < len(SUBSETS):
-                pending = _enqueue_subset_h2d(dev, acts[LINEARS[SUBSETS[si + 1][0]][3]], (si + 1) & 1)
+            Xd, ready, wdev, wev = pending
+            if si == 0:
+                mark("h2d subset 0 done", _copy_stream(dev))
+            if si + 1 < len(SUBSETS) or prefetch_next:      # the upload keeps running one subset ahead, across steps too
+                nxt = SUBSETS[(si + 1) % len(SUBSETS)]
+                pending = _enqueue_subset_h2d(dev, acts[LINEARS[nxt[0]][3]], [weights[li] for li in nxt], (si + 1) & 1)
+                mark(f"h2d subset {(si + 1) % len(SUBSETS)} done", _copy_stream(dev))
+            else:
+                pending = None
             for j in range(Xd.shape[0]):
                 cur.wait_event(ready[j])
                 xj = Xd[j].unsqueeze(0)
                 for g in gs:
                     g.add_batch(xj, None)
-            for g in gs:
-                g.raw_accumulator()                      # fold what is still staged, so the landing buffer is free
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            _H2D[dev]["consumed"][si & 1] = ev
+            mark(f"hessian subset {si} done", cur)
+            cur.wait_event(wev)                           # this subset's weights have landed
+            for g, wd in zip(gs, wdev):
+                g.layer.weight.data = wd
         else:
             for j in range(X.shape[0]):
                 xj = X[j].unsqueeze(0)
@@ -302,9 +333,18 @@ def quantize_layer(dev, acts, weights, world, from_host):
                 d2h += sum(o.numel() * o.element_size() for o in outs)
             results.append((qw, g.error))
             g.free()
-    if from_host:
+        if from_host:                                     # activations staged, weights read: the landing area is free
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            _H2D[dev]["consumed"][si & 1] = ev
+        mark(f"fasterquant subset {si} done", cur)
+    if from_host and pending is None:
         cur.wait_stream(_copy_stream(dev))
-    return results, d2h
+    if trace is not None:
+        torch.cuda.synchronize()
+        t0 = trace[0][1]
+        print("e2e trace (ms since step start): " + "; ".join(f"{n} {t0.elapsed_time(e):.1f}" for n, e in trace[1:]), file=sys.stderr)
+    return results, d2h, pending
 
 
 def run_ours(args):
@@ -335,6 +375,7 @@ def run_ours(args):
         with contextlib.redirect_stdout(quiet):
             for _ in range(warmup):
                 quantize_layer(dev, acts, weights, world, from_host)
+            carry = None
             barrier()
             G.PROFILE = [] if profile else None
             n0 = _lib.launch_count()
@@ -342,8 +383,8 @@ def run_ours(args):
             e1 = torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
-            for _ in range(steps):
-                _, d2h = quantize_layer(dev, acts, weights, world, from_host)
+            for i in range(steps):
+                _, d2h, carry = quantize_layer(dev, acts, weights, world, from_host, carry, prefetch_next=from_host and i + 1 < steps)
             e1.record()
             barrier()
             wall = time.perf_counter() - t0

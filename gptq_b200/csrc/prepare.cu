@@ -136,6 +136,18 @@ __global__ void stage_kernel(const T* __restrict__ src, int64_t tokens, int K, i
         dst[t * ldd + c] = (c < K) ? src[t * lds + c] : from_f32<T>(0.f);
 }
 
+// 16-byte vectorised variant (K, both pitches multiples of 8 elements, 16-byte aligned bases): grid-stride over rows.
+__global__ void __launch_bounds__(256)
+stage_vec_kernel(const uint4* __restrict__ src, int64_t tokens, int kv, int64_t lds_v, uint4* __restrict__ dst, int64_t ldd_v) {
+    // ldd_v >= kv: the pad vectors [kv, ldd_v) of every row are zeroed
+    for (int64_t t = blockIdx.y; t < tokens; t += gridDim.y) {
+        const uint4* s = src + t * lds_v;
+        uint4* d = dst + t * ldd_v;
+        for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ldd_v; c += gridDim.x * blockDim.x)
+            d[c] = (c < kv) ? s[c] : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
 // ------------------------------------------------------------------ exact (bitwise) comparison of two 16-bit batches
 // flag |= 1 when any element differs.  Used to verify that a batch handed to a second GPTQ object is the very
 // batch already staged by the first one before their Hessian accumulators are shared (gptq.py:38-65 computes
@@ -275,8 +287,17 @@ extern "C" int gptq_b200_stage_input(const void* src, int dtype, int64_t tokens,
     GQ_ARG(dst, 6, "null"); GQ_ARG(ld_dst >= K && ld_dst % 8 == 0, 7, "ld_dst must be >= K and a multiple of 8");
     if (tokens == 0) return 0;
     cudaStream_t st = as_stream(stream);
-    if (ld_src == K && ld_dst == K) {   // dense -> dense: one bulk device copy
-        GQ_CUDA(cudaMemcpyAsync(dst, src, (size_t)tokens * K * 2, cudaMemcpyDeviceToDevice, st));
+    // Always an SM copy, never cudaMemcpyAsync: a device-to-device memcpy is executed by a copy engine and queues behind
+    // whatever host-to-device transfers the caller has in flight on other streams (measured: it serialised the whole
+    // Hessian phase behind the activation upload).
+    if (K % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        const int kv = K / 8;
+        const int64_t ldd_v = ld_dst / 8;
+        int gx = cdiv(ldd_v, 256); if (gx > 4) gx = 4;
+        dim3 g(gx, (unsigned)(tokens > 1184 ? 1184 : tokens));
+        stage_vec_kernel<<<g, 256, 0, st>>>((const uint4*)src, tokens, kv, ld_src / 8, (uint4*)dst, ldd_v);
+        GQ_LAUNCHED();
         return 0;
     }
     dim3 g(cdiv(ld_dst, 256), (unsigned)(tokens > 4096 ? 4096 : tokens));

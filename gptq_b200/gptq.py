@@ -564,7 +564,9 @@ class GPTQ:
             _lib.check(lib.gptq_b200_finalize(Q.data_ptr(), K, codes.data_ptr(), K, R, K, _lib.ptr(invperm), Wout.data_ptr(),
                                               _lib.dt(Wout), K, codes_out.data_ptr(), K, st), "finalize")
 
-        torch.cuda.synchronize()                        # gptq.py:292
+        # gptq.py:292 calls torch.cuda.synchronize(); everything here was issued on the current stream, so that stream is
+        # what must drain -- a device-wide sync would also wait for unrelated streams (e.g. the caller's H2D prefetch)
+        torch.cuda.current_stream(dev).synchronize()
         self._release()
         if flag is not None and int(flag.item()) != 0:
             raise RuntimeError("GPTQ: a batch assumed identical for linears sharing one Hessian accumulator differed "

@@ -102,8 +102,11 @@ class Quantizer(nn.Module):
     def find_params(self, x, weight=True):
         _lib.require_cuda(x, "Quantizer.find_params: x")
         dev = x.device
-        self.maxq = self.maxq.to(dev)
         maxq = _as_int(self.maxq)
+        if self.maxq.device != dev:
+            # quant.py:39 moves the buffer with .to(dev); a fill kernel does the same without a host-to-device copy, which
+            # would queue behind whatever transfers the caller has in flight on other streams and stall this one
+            self.maxq = torch.full((), maxq, dtype=self.maxq.dtype, device=dev)
         shape = x.shape
         if self.perchannel:                                 # quant.py:42-52
             if weight:
