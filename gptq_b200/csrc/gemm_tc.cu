@@ -27,6 +27,7 @@ namespace gq {
 
 extern int g_gemm_splitk;
 extern int g_gemm_splitk_minkb;
+extern int g_gemm_trunc;
 
 constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 32;
 constexpr int GT_STAGES = 2;
@@ -42,6 +43,7 @@ constexpr int GT_TP = GT_BM + 4;                      // pitch of the transposed
 
 struct GemmTcParams {
     int M, N, Kd; float alpha, beta; float* C; int64_t ldc; int mode; int a_mn, b_mn; uint32_t idesc;
+    int trunc;                                        // 1: the MMA reads the raw fp32 tile as `hi` (see the converter)
     int splits;                                       // cluster size along z: the k-range of a tile is split over the cluster
 };
 
@@ -204,13 +206,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* hi = isA ? base + idx * 16 : base + 2 * GT_A_BYTES + (idx - GT_A_BYTES / 16) * 16;
                 uint8_t* lo = hi + (isA ? GT_A_BYTES : GT_B_BYTES);
                 float4 v = *reinterpret_cast<const float4*>(hi);
-                float4 h, l;                    // hi = rn_tf32(x); lo = rn_tf32(x - hi)  (x - hi is exact)
-                h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
-                h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
-                h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
-                h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
-                *reinterpret_cast<float4*>(hi) = h;
-                *reinterpret_cast<float4*>(lo) = l;
+                float4 h, l;
+                if (p.trunc) {
+                    // kind::tf32 ignores the 13 low mantissa bits of its 32-bit operands, so the raw tile already IS the
+                    // high part (hi = x with those bits cleared) and only lo = rn_tf32(x - hi) has to be written
+                    // (x - hi is exact).  One shared-memory store per element instead of two.
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = rn_tf32(v.x - h.x);
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = rn_tf32(v.y - h.y);
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = rn_tf32(v.z - h.z);
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = rn_tf32(v.w - h.w);
+                    *reinterpret_cast<float4*>(lo) = l;
+                } else {                        // hi = rn_tf32(x); lo = rn_tf32(x - hi)  (x - hi is exact)
+                    h.x = rn_tf32(v.x); l.x = rn_tf32(v.x - h.x);
+                    h.y = rn_tf32(v.y); l.y = rn_tf32(v.y - h.y);
+                    h.z = rn_tf32(v.z); l.z = rn_tf32(v.z - h.z);
+                    h.w = rn_tf32(v.w); l.w = rn_tf32(v.w - h.w);
+                    *reinterpret_cast<float4*>(hi) = h;
+                    *reinterpret_cast<float4*>(lo) = l;
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -381,6 +394,7 @@ int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, co
     if (g_gemm_splitk)
         while (S * 2 <= 8 && tiles * S * 2 <= num_sms() && nkb / (S * 2) >= g_gemm_splitk_minkb) S *= 2;
     p.splits = S;
+    p.trunc = g_gemm_trunc;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(gx, gy, S);
     cfg.blockDim = dim3(GT_THREADS, 1, 1);
@@ -419,6 +433,7 @@ static int int_from_env(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
 }
+int g_gemm_trunc = int_from_env("GPTQ_B200_GEMM_TRUNC", 1);            // see the converter in gemm_tc_kernel
 int g_gemm_splitk_minkb = int_from_env("GPTQ_B200_SPLITK_MINKB", 4);   // fewest k-blocks (of 32) a split may get
 int g_pdl = flag_from_env("GPTQ_B200_PDL", 1);
 

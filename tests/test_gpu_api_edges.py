@@ -54,7 +54,11 @@ def test_odd_shapes_match_oracle(R, K):
     bad_rows = int((g.codes.cpu() != ref.codes).any(dim=1).sum())
     assert bad_rows <= 1, bad_rows                                        # at most one rounding-tie flip
     if bad_rows == 0:
-        assert torch.equal(lin.weight.data.cpu(), ref.Q.half())
+        # identical codes; with dynamic groups the group scale is fitted to the lazily UPDATED weights (gptq.py:255), whose
+        # last fp32 bits depend on the summation order of the update GEMM, so the dequantised fp16 value may differ by an ulp
+        got, want = lin.weight.data.cpu().float(), ref.Q.half().float()
+        assert torch.allclose(got, want, rtol=2 ** -9, atol=1e-7)
+        assert (got == want).float().mean() >= 0.98
 
 
 def test_batched_3d_input_and_empty_batch():
