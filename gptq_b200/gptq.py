@@ -564,19 +564,39 @@ class GPTQ:
             _lib.check(lib.gptq_b200_finalize(Q.data_ptr(), K, codes.data_ptr(), K, R, K, _lib.ptr(invperm), Wout.data_ptr(),
                                               _lib.dt(Wout), K, codes_out.data_ptr(), K, st), "finalize")
 
-        # gptq.py:292 calls torch.cuda.synchronize(); everything here was issued on the current stream, so that stream is
-        # what must drain -- a device-wide sync would also wait for unrelated streams (e.g. the caller's H2D prefetch)
-        torch.cuda.current_stream(dev).synchronize()
+        # Everything that does not need a host value is queued BEFORE the one synchronisation point, so the device is not
+        # left idle while Python post-processes: outputs in the caller's column order, the quantizer state the reference
+        # leaves behind, and ONE small record (info, sharing flag, loss) that is read back with a single copy.
+        if gidx is None:
+            g_idx_out = torch.zeros(K, device=dev, dtype=torch.int32)
+        else:
+            g_idx_out = gidx[invperm.long()].contiguous() if actorder else gidx
+        q_after, q_scale, q_zero = q, None, None
+        if grouped:
+            # what `self.quantizer` holds after the run: the parameters of the group of the LAST processed
+            # column -- gidx is in processing order, so that group is gidx[K-1]
+            if static_groups:
+                q_after = copy.deepcopy(q)             # the reference swaps in groups[...] (a deepcopy), gptq.py:260
+            if static_groups and actorder:
+                last = gidx[K - 1:K].long()
+                q_scale, q_zero = scale.index_select(1, last), zero.index_select(1, last)
+            else:
+                q_scale, q_zero = scale[:, ng - 1:ng].clone(), zero[:, ng - 1:ng].clone()
+        rec = torch.cat([info.to(torch.float64), (flag if flag is not None else info.new_zeros(1)).to(torch.float64), loss])
+        # gptq.py:292 calls torch.cuda.synchronize(); everything here was issued on the current stream, so reading the
+        # record back (a stream-ordered blocking copy) is the synchronisation -- a device-wide sync would also wait for
+        # unrelated streams (e.g. the caller's H2D prefetch)
+        rec = rec.cpu()
         self._release()
-        if flag is not None and int(flag.item()) != 0:
+        if rec[1] != 0:
             raise RuntimeError("GPTQ: a batch assumed identical for linears sharing one Hessian accumulator differed "
                                "(the tensor was modified between their forward hooks); set GPTQ_B200_SHARE_H=0")
-        bad = int(info.item())
+        bad = int(rec[0])
         if bad != 0:
             raise torch.linalg.LinAlgError(
                 f"linalg.cholesky: The factorization could not be completed because the input is not positive-definite "
                 f"(the leading minor of order {bad} is not positive-definite).")
-        self.error = float(loss.item())
+        self.error = float(rec[2])
         print('time %.2f' % (time.time() - tick))
         print('error', self.error)
 
@@ -585,24 +605,16 @@ class GPTQ:
                 Wfull = Wout.t()
             else:
                 Wfull = Wout
-            self.layer.weight.data = Wfull.reshape(self.layer.weight.shape).to(wdtype)
+            self.layer.weight.data = Wfull.reshape(self.layer.weight.shape)
         self.Wq = Wout                                  # [rows(shard), K] dequantised weights in the layer dtype
         self.codes = codes_out
         self.scales = scale
         self.zeros = zero
         self.perm = perm
-        if gidx is None:
-            self.g_idx = torch.zeros(K, device=dev, dtype=torch.int32)
-        else:
-            self.g_idx = gidx[invperm.long()].contiguous() if actorder else gidx
-        # what `self.quantizer` holds after the run: the last group's parameters
-        if grouped:
-            last = int(self.g_idx[int(perm[K - 1].item())].item()) if (static_groups and actorder) else ng - 1
-            if static_groups:
-                q = copy.deepcopy(q)                   # the reference swaps in groups[...] (a deepcopy), gptq.py:260
-                self.quantizer = q
-            q.scale = scale[:, last:last + 1].clone()
-            q.zero = zero[:, last:last + 1].clone()
+        self.g_idx = g_idx_out
+        if q_scale is not None:
+            q_after.scale, q_after.zero = q_scale, q_zero
+        self.quantizer = q_after
         if DEBUG:
             print(torch.sum((self.layer(self.inp1) - self.out1) ** 2))
 
