@@ -72,8 +72,10 @@ blockquant_kernel(BQArgs a) {
     const bool rvalid = row < a.R;
     const int count = a.count, i1 = a.i1;
     ptx::pdl_launch_dependents();
-    ptx::pdl_wait();                         // W carries the preceding lazy-update GEMM.  An early-launched kernel does not
-                                             // start with a clean L1: everything mutable is read with ld.global.cg (L2)
+    // Programmatic dependent launch: this kernel may start while the preceding lazy-update GEMM is still running.  Hinv1,
+    // gidx and the quantizer tables do not change during the column loop (mode 0; mode 1 is launched fully serialized),
+    // so they are staged BEFORE the wait and overlap the GEMM's tail; only W is read after it (through L2: an
+    // early-launched kernel does not start with a clean L1).
 
     // ---- stage Hinv1 = U[i1:i1+count, i1:i1+count] (zero padded); independent loads, unrolled for memory-level parallelism
     const bool uvec = ((a.ldu & 3) == 0) && ((i1 & 3) == 0) && ((((uintptr_t)a.U) & 15) == 0);
@@ -135,6 +137,7 @@ blockquant_kernel(BQArgs a) {
             }
         }
     }
+    ptx::pdl_wait();
     // ---- W1 slice -> registers: w[kk*4+v] = W[row][i1 + kk*CW + l4*4 + v]
     float w[NW];
     uint32_t cpk[NCH];

@@ -28,6 +28,7 @@ namespace gq {
 extern int g_gemm_splitk;
 extern int g_gemm_splitk_minkb;
 extern int g_gemm_trunc;
+extern int g_small_gemm_max;
 
 constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 32;
 constexpr int GT_STAGES = 2;
@@ -433,12 +434,17 @@ static int int_from_env(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
 }
+int g_small_gemm_max = int_from_env("GPTQ_B200_SMALL_GEMM_MAX", 512);   // M, N up to which gemm_fp32 uses sgemm_small.cu
 int g_gemm_trunc = int_from_env("GPTQ_B200_GEMM_TRUNC", 1);            // see the converter in gemm_tc_kernel
 int g_gemm_splitk_minkb = int_from_env("GPTQ_B200_SPLITK_MINKB", 4);   // fewest k-blocks (of 32) a split may get
 int g_pdl = flag_from_env("GPTQ_B200_PDL", 1);
 
 int gemm_fp32(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda, const float* B,
               int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st) {
+    // measured on B200 (tools/perf_probe.py hinv): the small-tile kernel wins up to 384x512 outputs, the tensor-core
+    // kernel (with split-K) from 512x512 on
+    if (M <= g_small_gemm_max && N <= g_small_gemm_max && (int64_t)M * N < (int64_t)g_small_gemm_max * g_small_gemm_max)
+        return sgemm_small_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, mode, st);
     if (g_gemm_backend == 1 && gemm_tc_supported(A, lda, B, ldb, C, ldc))
         return gemm_tc_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, mode, st);
     return sgemm_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, mode, st);

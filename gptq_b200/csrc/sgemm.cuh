@@ -23,6 +23,10 @@ namespace gq {
 bool gemm_tc_supported(const float* A, int64_t lda, const float* B, int64_t ldb, const float* C, int64_t ldc);
 int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda,
                    const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st);
+// Small-tile CUDA-core variant (sgemm_small.cu) for products whose M and N are at most a couple of hundred: the low
+// levels of the chain recursion, where the tensor-core kernel's fixed cost dominates.
+int sgemm_small_launch(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda,
+                       const float* B, int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st);
 // Backend selection used by the chain and the lazy update: 1 = tensor cores when supported (default), 0 = CUDA cores.
 extern int g_gemm_backend;
 int gemm_fp32(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda,
