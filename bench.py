@@ -47,6 +47,26 @@ GPTQ_KW = dict(blocksize=128, percdamp=.01, groupsize=128, actorder=True, static
 WBITS = 4
 
 
+def syrk_traffic(prof):
+    """Launch-weighted DRAM bytes per syrk launch of the timed region, from the committed ncu capture
+    (profiles/r01_syrk_traffic.json: per launch shape).  None if a launch shape was not captured."""
+    path = os.path.join(ROOT, "profiles", "r01_syrk_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        shapes = json.load(f)["launch_shapes"]
+    tot, n = 0.0, 0
+    for name, _, _, work, meta in prof:
+        if name != "syrk":
+            continue
+        ent = shapes.get("K%d_T%d" % meta) if meta else None
+        if ent is None:
+            return None
+        tot += ent["dram_read_bytes"] + ent["dram_write_bytes"]
+        n += 1
+    return tot / n if n else None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -408,7 +428,7 @@ def run_ours(args):
 
     # per-kernel device time inside the timed region (CUDA events on the launching stream)
     agg = {}
-    for name, a, b, work in prof:
+    for name, a, b, work, _meta in prof:
         d = agg.setdefault(name, [0.0, 0.0, 0])
         d[0] += a.elapsed_time(b)
         d[1] += work
@@ -420,7 +440,9 @@ def run_ours(args):
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": syrk_tflops / pk["tf_sustained"],
                 "peak_source": pk["source"] + " bf16 cuBLAS sustained", "frac_of_nominal_2250": syrk_tflops / 2250.0,
                 "launches": sy[2], "avg_launch_ms": sy[0] / max(sy[2], 1), "share_of_step": sy[0] / ms,
-                "dense_equivalent_tflops": dense_equiv, "traffic": None}
+                "dense_equivalent_tflops": dense_equiv, "traffic": syrk_traffic(prof) if world == 1 else None,
+                "traffic_note": "DRAM read+write bytes per launch (launch-weighted over the K=4096 and K=11008 launches) from the "
+                                "committed ncu capture profiles/r01_syrk_traffic.json; algorithmic bytes per launch: 0.40 GB / 1.22 GB"}
     co = agg.get("colloop", [1e-9, 0.0, 1])
     hv = agg.get("hinv_upper", [1e-9, 0.0, 1])
     others = {

@@ -64,8 +64,8 @@ PROFILE = None
 
 
 class _prof:
-    def __init__(self, name, work=0.0):
-        self.name, self.work = name, work
+    def __init__(self, name, work=0.0, meta=None):
+        self.name, self.work, self.meta = name, work, meta
 
     def __enter__(self):
         if PROFILE is not None:
@@ -77,7 +77,7 @@ class _prof:
     def __exit__(self, *exc):
         if PROFILE is not None:
             self.b.record()
-            PROFILE.append((self.name, self.a, self.b, self.work))
+            PROFILE.append((self.name, self.a, self.b, self.work, self.meta))
         return False
 
 
@@ -212,7 +212,7 @@ class _Accumulator:
         need = lib.gptq_b200_syrk_workspace_bytes(K, self.staged)
         if need and (self.ws is None or self.ws.numel() < need):
             self.ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        with _prof("syrk", syrk_issued_flops(K, self.staged)):
+        with _prof("syrk", syrk_issued_flops(K, self.staged), (K, self.staged)):
             _lib.check(lib.gptq_b200_syrk_accum(self.stage.data_ptr(), _lib.dt(self.stage), self.staged, K,
                                                 self.stage.stride(0), self.S.data_ptr(), K, 1.0, 1.0, CHUNK_TOKENS,
                                                 _lib.ptr(self.ws) if need else 0, need, _lib.stream()), "syrk_accum")
