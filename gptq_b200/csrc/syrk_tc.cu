@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace gq {
 
@@ -45,16 +46,17 @@ struct SyrkParams {
     float* H; int64_t ldh; float alpha; float beta;
     float* partial;             // [splits][n_tiles][128][256] when splits > 1
     uint32_t idesc;
+    int sw, sh;                 // tile-order chunk: column blocks x row blocks (see decode_tile)
 };
 
 // Tile order.  Valid tiles are (bi, bj) with bi >= 2 bj (128-row x 256-column tiles touching the lower triangle).
 // The CTAs of one wave run consecutive items in lockstep over the tokens, so what matters for HBM traffic is how many
 // DISTINCT channel panels a wave touches: enumerating column by column makes a wave read ~nbm row panels (all of X,
 // over and over: ncu measured 10.8 GB of DRAM reads for the 721 MB slab at K = 11008).  Instead the tiles are walked
-// in 2-D chunks of SY_SW column blocks x SY_SH row blocks (~one wave: 24 x 128 + 6 x 256 = 4608 channels).
-constexpr int SY_SW = 6, SY_SH = 24;
+// in 2-D chunks of sw column blocks x sh row blocks (default 12 x 12 = 144 tiles, ~one wave: 12 x 128 + 12 x 256 = 4608
+// channels; 6 x 24 and 16 x 9 measured 1-2 % slower).
 
-__device__ __forceinline__ void decode_tile(int t, int nbm, int& bi, int& bj) {
+__device__ __forceinline__ void decode_tile(int t, int nbm, int SY_SW, int SY_SH, int& bi, int& bj) {
     const int nbn = (nbm + 1) >> 1;
     for (int sc = 0; sc < nbn; sc += SY_SW) {
         const int w = min(SY_SW, nbn - sc);
@@ -107,7 +109,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
             int stage = 0; uint32_t phase = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int tile = item / p.splits, split = item - tile * p.splits;
-                int bi, bj; decode_tile(tile, p.nbm, bi, bj);
+                int bi, bj; decode_tile(tile, p.nbm, p.sw, p.sh, bi, bj);
                 const bool a_in_b = (bi >> 1) == bj;
                 const int64_t t0 = (int64_t)split * p.tokens_per_split;
                 const int64_t t1 = min(t0 + p.tokens_per_split, p.T);
@@ -134,7 +136,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
             int buf = 0; uint32_t bphase[2] = {0, 0};
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 const int tile = item / p.splits, split = item - tile * p.splits;
-                int bi, bj; decode_tile(tile, p.nbm, bi, bj);
+                int bi, bj; decode_tile(tile, p.nbm, p.sw, p.sh, bi, bj);
                 const bool a_in_b = (bi >> 1) == bj;
                 const int a_off = a_in_b ? (SY_A_BYTES + (bi & 1) * 2 * SY_PANEL) : 0;
                 const int64_t t0 = (int64_t)split * p.tokens_per_split;
@@ -177,7 +179,7 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
         const bool hvec = ((p.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.H) & 15) == 0);
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int tile = item / p.splits, split = item - tile * p.splits;
-            int bi, bj; decode_tile(tile, p.nbm, bi, bj);
+            int bi, bj; decode_tile(tile, p.nbm, p.sw, p.sh, bi, bj);
             const int64_t t0 = (int64_t)split * p.tokens_per_split;
             const int64_t t1 = min(t0 + p.tokens_per_split, p.T);
             float acc[128];
@@ -253,9 +255,9 @@ syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, const SyrkParams p) {
 // H = beta*H + alpha * sum_s partial[s][tile]   (fixed summation order)
 __global__ void __launch_bounds__(256)
 syrk_reduce_kernel(const float* __restrict__ partial, int n_tiles, int splits, int nbm, int K, float* __restrict__ H,
-                   int64_t ldh, float alpha, float beta) {
+                   int64_t ldh, float alpha, float beta, int sw, int sh) {
     const int tile = blockIdx.x;
-    int bi, bj; decode_tile(tile, nbm, bi, bj);
+    int bi, bj; decode_tile(tile, nbm, sw, sh, bi, bj);
     for (int e = threadIdx.x; e < SY_BM * SY_BN; e += 256) {
         int r = e >> 8, c = e & 255;
         int gr = bi * SY_BM + r, gc = bj * SY_BN + c;
@@ -394,12 +396,21 @@ extern "C" int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, in
     p.H = H; p.ldh = ldh; p.alpha = alpha; p.beta = beta;
     p.partial = static_cast<float*>(ws);
     p.idesc = ptx::make_idesc(dtype == GPTQ_B200_F16 ? 0 : 1, 1, 1, SY_BM, SY_BN);
+    {
+        static int sw = 0, sh = 0;
+        if (!sw) {
+            const char* e1 = getenv("GPTQ_B200_SYRK_SW"); const char* e2 = getenv("GPTQ_B200_SYRK_SH");
+            sw = e1 ? atoi(e1) : 12; sh = e2 ? atoi(e2) : 12;
+            if (sw < 1) sw = 1; if (sh < 1) sh = 1;
+        }
+        p.sw = sw; p.sh = sh;
+    }
     const int n_items = pl.n_tiles * pl.splits;
     const int grid = n_items < num_sms() ? n_items : num_sms();
     syrk_tc_kernel<<<grid, SY_THREADS, SY_SMEM, st>>>(tmap, p);
     GQ_LAUNCHED();
     if (pl.splits > 1) {
-        syrk_reduce_kernel<<<pl.n_tiles, 256, 0, st>>>(p.partial, pl.n_tiles, pl.splits, pl.nbm, K, H, ldh, alpha, beta);
+        syrk_reduce_kernel<<<pl.n_tiles, 256, 0, st>>>(p.partial, pl.n_tiles, pl.splits, pl.nbm, K, H, ldh, alpha, beta, p.sw, p.sh);
         GQ_LAUNCHED();
     }
     return 0;

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gq::|blockquant|chol_diag|gemm_tc|syrk" -c 6000 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1580 -c 4000 --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:syrk_tc -s 8 -c 1 -f -o gpurun_out/prof_syrk_k4096 \
     python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e > gpurun_out/ncu_syrk1.log 2>&1
