@@ -74,8 +74,8 @@ def load() -> C.CDLL:
             fn.restype = res
             fn.argtypes = args
         ver = lib.gptq_b200_abi_version()
-        if ver != 1:
-            raise GptqB200Error(f"ABI version mismatch: library {ver}, binding 1")
+        if ver != 2:
+            raise GptqB200Error(f"ABI version mismatch: library {ver}, binding 2")
         _lib = lib
     return _lib
 

@@ -35,7 +35,7 @@ constexpr int BQ_MAX_ROWS = 96;      // rows per CTA: 64 KB + 3 * rows * 516 B o
 struct BQArgs {
     float* W; int R; int K; int64_t ldw; const float* U; int64_t ldu; int i1; int count;
     const int32_t* gidx; const float* scale; const float* zero; int ng; float maxq; int trits;
-    float* Q; int64_t ldq; uint8_t* codes; int64_t ldc; float* Err; int64_t lde; double* loss; int rows_per_cta;
+    float* Q; int64_t ldq; uint8_t* codes; int64_t ldc; float* Err; int64_t lde; float* row_loss; int rows_per_cta;
 };
 
 // Exactly rounded a / b given y = RN(1 / b): two residual-correction passes.
@@ -64,7 +64,6 @@ blockquant_kernel(BQArgs a) {
     float* Zs = Ss + RPC * BQ_SP;            // [RPC][129]  zero
     float* Ys = Zs + RPC * BQ_SP;            // [RPC][129]  RN(1/scale)
     __shared__ float s_rd[BQ_B];             // RN(1 / Hinv1[i][i])
-    __shared__ double s_loss[BQ_MAX_ROWS * 4 / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
     const int l4 = lane & (LPR - 1), rl = tid / LPR;
@@ -242,16 +241,9 @@ blockquant_kernel(BQArgs a) {
             }
         }
     }
-    double dl = (rvalid && l4 == 0) ? (double)loss : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dl += __shfl_xor_sync(0xffffffffu, dl, o);
-    if (lane == 0) s_loss[warp] = dl;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0.0;
-        for (int i = 0; i < (nthreads >> 5); ++i) t += s_loss[i];
-        atomicAdd(a.loss, t * 0.5);                                      // Losses1 / 2, gptq.py:274
-    }
+    // Losses1 / 2 (gptq.py:274), accumulated per row over the blocks: one owner lane per row, launches are serialized,
+    // so the sum is deterministic (the caller reduces rows, or row ranges, in double).
+    if (rvalid && l4 == 0) a.row_loss[row] = __ldcg(&a.row_loss[row]) + 0.5f * loss;
 }
 
 static int bq_lpr8_from_env() {
@@ -294,7 +286,7 @@ extern "C" size_t gptq_b200_colloop_workspace_bytes(int R, int K, int blocksize)
 extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const float* U, int64_t ldu, int blocksize,
                                  int groupsize, int mode, const int32_t* gidx, float* scale, float* zero, int ngroups,
                                  int maxq, int sym, int mse, float norm, int grid, float maxshrink, float* Q, int64_t ldq,
-                                 uint8_t* codes, int64_t ldc, double* loss, void* ws, size_t ws_bytes, void* stream) {
+                                 uint8_t* codes, int64_t ldc, float* row_loss, void* ws, size_t ws_bytes, void* stream) {
     GQ_ARG(W, 1, "null"); GQ_ARG(R >= 0, 2, "R<0"); GQ_ARG(K > 0, 3, "K<=0"); GQ_ARG(ldw >= K, 4, "ldw<K");
     GQ_ARG(U, 5, "null"); GQ_ARG(ldu >= K, 6, "ldu<K");
     GQ_ARG(blocksize > 0 && blocksize <= BQ_B, 7, "blocksize must be in [1,128]");
@@ -304,7 +296,7 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
     GQ_ARG(ngroups == 1 || gidx, 10, "gidx required when ngroups > 1");
     GQ_ARG(maxq != 0, 14, "maxq == 0 (Quantizer not configured)");
     GQ_ARG(Q, 20, "null"); GQ_ARG(ldq >= K, 21, "ldq<K"); GQ_ARG(codes, 22, "null"); GQ_ARG(ldc >= K, 23, "ldc<K");
-    GQ_ARG(loss, 24, "null"); GQ_ARG(ws, 25, "null");
+    GQ_ARG(row_loss, 24, "null"); GQ_ARG(ws, 25, "null");
     GQ_ARG(ws_bytes >= gptq_b200_colloop_workspace_bytes(R, K, blocksize), 26, "workspace too small");
     if (R == 0) return 0;
     cudaStream_t st = as_stream(stream);
@@ -322,7 +314,7 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
         attr_done = true;
     }
     const int lpr = (rpc <= g_bq_lpr8_max_rows) ? 8 : 4;
-    GQ_CUDA(cudaMemsetAsync(loss, 0, sizeof(double), st));
+    GQ_CUDA(cudaMemsetAsync(row_loss, 0, (size_t)R * sizeof(float), st));
     // Two-level lazy update (same arithmetic as gptq.py:276, regrouped): after every block only the rest of the current
     // super-block is brought up to date (narrow GEMM, depth `count`); the columns beyond it receive ONE deep GEMM per
     // super-block.  Dynamic groups wider than a block read W far ahead (gptq.py:255), so they keep the one-level form.
@@ -346,7 +338,7 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
         }
         float* Eblk = Err + (i1 - sb_start);
         BQArgs a{W, R, K, ldw, U, ldu, i1, count, gidx, scale, zero, ngroups, (float)maxq, maxq < 0 ? 1 : 0,
-                 Q, ldq, codes, ldc, Eblk, lde, loss, rpc};
+                 Q, ldq, codes, ldc, Eblk, lde, row_loss, rpc};
         if (lpr == 8) GQ_CUDA(launch_pdl(/*allow=*/i1 > 0 && mode == 0, blockquant_kernel<8>, dim3(cdiv(R, rpc)), dim3(rpc * 8), smem, st, a));
         else GQ_CUDA(launch_pdl(/*allow=*/i1 > 0 && mode == 0, blockquant_kernel<4>, dim3(cdiv(R, rpc)), dim3(rpc * 4), smem, st, a));
         GQ_LAUNCHED();

@@ -56,6 +56,9 @@ EMPTY_CACHE_ON_FREE = os.environ.get("GPTQ_B200_EMPTY_CACHE", "0") == "1"
 # checked at fasterquant's own host sync: a mismatch raises instead of producing a different result).
 SHARE_H = os.environ.get("GPTQ_B200_SHARE_H", "1") == "1"
 SHARE_VERIFY = os.environ.get("GPTQ_B200_SHARE_VERIFY", "1") == "1"
+# Linears that share a Hessian and are quantized with the same arguments are solved in ONE column loop (their rows
+# stacked): the loop is latency-bound, so three 4096-row linears cost little more than one.
+GROUP_SIBLINGS = os.environ.get("GPTQ_B200_GROUP_SIBLINGS", "1") == "1"
 
 
 # Optional per-call device timing: set ``gptq_b200.gptq.PROFILE = []`` and every C-ABI hot call appends
@@ -139,6 +142,8 @@ class _Accumulator:
         self.H = None                  # (2/n) S, mirrored, dead diagonal fixed -- after seal()
         self.dead = None
         self.solves = {}               # (percdamp, actorder) -> prologue + chain results
+        self.member_refs = []          # weakrefs of the GPTQ objects holding this accumulator
+        self.spec = {}                 # id(GPTQ) -> (arguments, weights, results) solved ahead by a sibling
 
     # -------------------------------------------------------------- accumulate
     def absorb(self, x, tmp, key, joinable):
@@ -307,6 +312,120 @@ def _solve_hessian(H, K, percdamp, actorder, dead=None):
     return dict(dead=dead, perm=perm, invperm=invperm, U=U, info=info, Kp=Kp)
 
 
+def _solve_rows(Ws, sol, qcfg, blocksize, groupsize, actorder, static_groups, wdtype, preset=None):
+    """fasterquant's per-row part (gptq.py:130-145 W.float() + dead columns, 157-163 static groups, 168 permute,
+    181-185 full-row find_params, 191-276 column loop, 300-305 un-permute + cast) for the rows of one or several linears
+    that share the solve `sol`, stacked into ONE matrix: rows are independent, so the results are cut back per linear.
+    Everything is queued on the current stream; nothing is read back.  Returns one dict of device tensors per linear."""
+    lib = _lib.load()
+    st = _lib.stream()
+    maxq, _perch, sym, mse, norm, grid, maxshrink = qcfg
+    dead, perm, invperm, U, Kp = (sol[k] for k in ("dead", "perm", "invperm", "U", "Kp"))
+    dev = U.device
+    K = Ws[0].shape[1]
+    Rs = [w.shape[0] for w in Ws]
+    R = sum(Rs)
+    f32 = dict(device=dev, dtype=torch.float32)
+    with _prof("prologue"):
+        W32 = torch.empty((R, K), **f32)
+        r0 = 0
+        for w in Ws:
+            _lib.check(lib.gptq_b200_weights_prepare(w.data_ptr(), _lib.dt(w), w.shape[0], K, w.stride(0), dead.data_ptr(),
+                                                     W32[r0:].data_ptr(), K, st), "weights_prepare")
+            r0 += w.shape[0]
+        _dbg("weights_prepare")
+        grouped = groupsize != -1
+        ng = 1 if not grouped else (K + groupsize - 1) // groupsize
+        gscale = gzero = None
+        if static_groups and grouped:               # gptq.py:157-163, on the un-permuted, un-updated W
+            gscale, gzero = find_params_groups(W32, maxq, sym, mse, norm, grid, maxshrink, groupsize)
+            _dbg("find_params_groups")
+        if actorder:                                # gptq.py:168
+            Wp = torch.empty_like(W32)
+            _lib.check(lib.gptq_b200_permute_cols(W32.data_ptr(), R, K, K, perm.data_ptr(), Wp.data_ptr(), K, st),
+                       "permute_cols")
+            del W32
+        else:
+            Wp = W32
+    if preset is None:
+        # gptq.py:181-185: the quantizer is not ready -> find_params on the whole (permuted) rows (one pair per row)
+        if _perch:
+            full_scale, full_zero = find_params_groups(Wp, maxq, sym, mse, norm, grid, maxshrink)
+            full_scale, full_zero = full_scale.reshape(R, 1), full_zero.reshape(R, 1)
+        else:                                       # quant.py:53-54,97-103: one pair per linear, repeated over its rows
+            parts, r0 = [], 0
+            for Rm in Rs:
+                tq = Quantizer()
+                tq.maxq = torch.tensor(maxq)
+                tq.perchannel, tq.sym, tq.mse, tq.norm, tq.grid, tq.maxshrink = False, sym, mse, norm, grid, maxshrink
+                tq.find_params(Wp[r0:r0 + Rm], weight=True)
+                parts.append((tq.scale.reshape(Rm, 1), tq.zero.reshape(Rm, 1)))
+                r0 += Rm
+            full_scale = torch.cat([p[0] for p in parts], 0)
+            full_zero = torch.cat([p[1] for p in parts], 0)
+        row_scale, row_zero = full_scale, full_zero
+    else:                                           # a quantizer that is ready() keeps its parameters (single linear only)
+        full_scale = full_zero = None
+        row_scale = preset[0].to(dev).reshape(R, 1).float().contiguous()
+        row_zero = preset[1].to(dev).reshape(R, 1).float().contiguous()
+
+    if not grouped:
+        mode = 0
+        scale, zero = row_scale.clone(), row_zero.clone()
+        gidx = None
+    elif static_groups:
+        mode = 0
+        scale, zero = gscale, gzero
+        cols = perm.long() if actorder else torch.arange(K, device=dev)
+        gidx = (cols // groupsize).to(torch.int32).contiguous()
+    else:
+        mode = 1
+        scale = torch.zeros((R, ng), **f32)
+        zero = torch.zeros((R, ng), **f32)
+        gidx = (torch.arange(K, device=dev) // groupsize).to(torch.int32).contiguous()
+
+    Q = torch.empty((R, K), **f32)
+    codes = torch.empty((R, K), device=dev, dtype=torch.uint8)
+    row_loss = torch.empty(R, **f32)
+    nws = lib.gptq_b200_colloop_workspace_bytes(R, K, blocksize)
+    ws = torch.empty(max(nws, 16), device=dev, dtype=torch.uint8)
+    # algorithmic bytes of the column loop (SURVEY 8d): W fp16 in, U upper fp32, Q fp16 + codes out
+    with _prof("colloop", 2.0 * R * K + 2.0 * K * (K + 1) + 2.0 * R * K + R * K + 8.0 * R * ng):
+        _lib.check(lib.gptq_b200_colloop(Wp.data_ptr(), R, K, K, U.data_ptr(), Kp, blocksize, groupsize, mode,
+                                         _lib.ptr(gidx), scale.data_ptr(), zero.data_ptr(), ng, maxq, int(sym),
+                                         int(mse), float(norm), int(grid), float(maxshrink), Q.data_ptr(), K,
+                                         codes.data_ptr(), K, row_loss.data_ptr(), ws.data_ptr(), nws, st), "colloop")
+
+    # gptq.py:300-305: un-permute and write back in the layer's dtype
+    Wout = torch.empty((R, K), device=dev, dtype=wdtype)
+    codes_out = torch.empty((R, K), device=dev, dtype=torch.uint8)
+    with _prof("epilogue", 4.0 * R * K + R * K + 2.0 * R * K + R * K):
+        _lib.check(lib.gptq_b200_finalize(Q.data_ptr(), K, codes.data_ptr(), K, R, K, _lib.ptr(invperm), Wout.data_ptr(),
+                                          _lib.dt(Wout), K, codes_out.data_ptr(), K, st), "finalize")
+    if gidx is None:
+        g_idx_out = torch.zeros(K, device=dev, dtype=torch.int32)
+    else:
+        g_idx_out = gidx[invperm.long()].contiguous() if actorder else gidx
+    q_scale = q_zero = None
+    if grouped:
+        # the group of the LAST processed column -- gidx is in processing order, so that group is gidx[K-1]
+        if static_groups and actorder:
+            last = gidx[K - 1:K].long()
+            q_scale, q_zero = scale.index_select(1, last), zero.index_select(1, last)
+        else:
+            q_scale, q_zero = scale[:, ng - 1:ng].clone(), zero[:, ng - 1:ng].clone()
+    outs, r0 = [], 0
+    for Rm in Rs:
+        sl = slice(r0, r0 + Rm)
+        outs.append(dict(Wout=Wout[sl], codes=codes_out[sl], scale=scale[sl], zero=zero[sl], g_idx=g_idx_out,
+                         loss=row_loss[sl].double().sum().reshape(1),
+                         full_scale=None if full_scale is None else full_scale[sl],
+                         full_zero=None if full_zero is None else full_zero[sl],
+                         q_scale=None if q_scale is None else q_scale[sl], q_zero=None if q_zero is None else q_zero[sl]))
+        r0 += Rm
+    return outs
+
+
 class GPTQ:
 
     def __init__(self, layer):
@@ -361,11 +480,13 @@ class GPTQ:
                 if (cand is not None and cand.K == self.columns and cand.count == tmp and cand.batches == 1
                         and cand.last_in_slab and not cand.sealed):
                     cand.members += 1
+                    cand.member_refs.append(weakref.ref(self))
                     cand.verify(x)
                     self._acc = cand
                     self.nsamples += tmp
                     return
             acc = self._acc = _Accumulator(self.columns, self.dev)
+            acc.member_refs.append(weakref.ref(self))
             acc.count = self.nsamples                             # (non-zero only if the caller preset nsamples)
         elif acc.members > 1:
             if shareable and acc.key == key and acc.count == self.nsamples + tmp and acc.last_in_slab:
@@ -401,12 +522,17 @@ class GPTQ:
         new.batches = max(acc.batches, 2)
         new.flag = acc.flag
         acc.members -= 1
+        acc.member_refs = [r for r in acc.member_refs if r() is not None and r() is not self]
+        acc.spec.pop(id(self), None)
+        new.member_refs.append(weakref.ref(self))
         self._acc = new
 
     def _release(self):
         acc, self._acc = self._acc, None
         if acc is not None:
             acc.members -= 1
+            acc.member_refs = [r for r in acc.member_refs if r() is not None and r() is not self]
+            acc.spec.pop(id(self), None)
             if acc.members <= 0:
                 acc._unregister()
 
@@ -415,6 +541,7 @@ class GPTQ:
         acc = self._acc
         if acc is None:
             acc = self._acc = _Accumulator(self.columns, self.dev)
+            acc.member_refs.append(weakref.ref(self))
             acc.count = self.nsamples
         elif acc.members > 1 and acc.count != self.nsamples and not acc.reduced and not acc.sealed:
             self._fork()
@@ -459,6 +586,52 @@ class GPTQ:
         return acc.S
 
     # ------------------------------------------------------------------ solve (gptq.py:126-309)
+    def _weight_rows(self, row_range):
+        """The layer's weight as [rows, K] (Conv2d flattened, Conv1D transposed), optionally a row shard."""
+        W = self.layer.weight.data
+        if isinstance(self.layer, nn.Conv2d):
+            W = W.flatten(1)
+        if isinstance(self.layer, _Conv1D):
+            W = W.t()
+        if row_range is not None:                       # row sharding: rows are independent given H (SURVEY 8e)
+            W = W[row_range[0]:row_range[1]]
+        return W.contiguous()
+
+    @staticmethod
+    def _qcfg(q):
+        return (int(q.maxq.item()), bool(q.perchannel), bool(q.sym), bool(q.mse), float(q.norm), int(q.grid),
+                float(q.maxshrink))
+
+    def _siblings_to_solve_with(self, acc, argkey, R):
+        """Linears that share this Hessian (hence U) and would be solved with exactly the same arguments: their rows are
+        independent of ours given U (gptq.py:191-276 acts row-wise), so they ride along in the same column loop -- the
+        loop is latency-bound, a few thousand extra rows cost little -- and their results wait in the accumulator until
+        their own fasterquant call asks for them (with the same arguments and bit-identical weights)."""
+        if not GROUP_SIBLINGS or acc is None or acc.members <= 1:
+            return []
+        sibs = []
+        total = R
+        # measured on B200: stacking pays only while the stacked slab per SM stays on the 8-lanes-per-row kernel (<= 40 rows
+        # per CTA), i.e. for row shards of 4+ GPUs or small models; at 4096 rows per linear it is a wash (the siblings'
+        # calls become pure host latency), so it is not done there
+        limit = 40 * torch.cuda.get_device_properties(self.dev).multi_processor_count
+        for ref in list(acc.member_refs):
+            g = ref()
+            if g is None or g is self or g._acc is not acc or g._consumed or g._H is not None or id(g) in acc.spec:
+                continue
+            if g.nsamples != self.nsamples or g.rows != self.rows or g.columns != self.columns:
+                continue
+            if type(g.layer) is not type(self.layer) or g.layer.weight.dtype != self.layer.weight.dtype:
+                continue
+            q = g.quantizer
+            if not isinstance(q, Quantizer) or q.ready() or self._qcfg(q) != argkey[-1]:
+                continue
+            if total + R > limit:
+                break
+            sibs.append(g)
+            total += R
+        return sibs
+
     def fasterquant(self, blocksize=128, percdamp=.01, groupsize=-1, actorder=False, static_groups=False,
                     model_name="opt", layer_name="layer", lut_quant=False, non_linear_quant=False, columnwise=False,
                     row_range=None):
@@ -467,30 +640,26 @@ class GPTQ:
                                       "outside the GPTQ hot path (SURVEY 8a)")
         if not isinstance(self.quantizer, Quantizer):
             raise TypeError("GPTQ.quantizer must be a gptq_b200.quant.Quantizer")
-        lib = _lib.load()
-        st = _lib.stream()
+        _lib.load()
         dev = self.dev
         q = self.quantizer
         K = self.columns
-        W = self.layer.weight.data
-        if isinstance(self.layer, nn.Conv2d):
-            W = W.flatten(1)
-        if isinstance(self.layer, _Conv1D):
-            W = W.t()
-        if row_range is not None:                       # row sharding: rows are independent given H
-            W = W[row_range[0]:row_range[1]]
-        W = W.contiguous()
+        W = self._weight_rows(row_range)
         R = W.shape[0]
-        maxq = int(q.maxq.item())
-        if maxq == 0:
+        qcfg = self._qcfg(q)
+        if qcfg[0] == 0:
             raise RuntimeError("Quantizer.configure() was not called")
+        argkey = (int(blocksize), float(percdamp), int(groupsize), bool(actorder), bool(static_groups),
+                  None if row_range is None else tuple(row_range), qcfg)
 
         tick = time.time()
         if self._consumed:
             raise RuntimeError("fasterquant: H was already consumed or freed")
+        out = None
         if self._H is not None:                         # a user-provided / already materialised H (gptq.py:141-142)
             sol = _solve_hessian(self._H, K, percdamp, actorder)
             flag = None
+            sibs = []
         else:                                           # the accumulator, finished in place; siblings reuse the solve
             acc = self._own_accumulator()
             H = acc.seal(self.nsamples)
@@ -500,93 +669,28 @@ class GPTQ:
             if sol is None:
                 sol = acc.solves[skey] = _solve_hessian(H, K, percdamp, actorder, dead=acc.dead)
             flag = acc.flag
-            del H, acc
+            ent = acc.spec.pop(id(self), None)          # solved ahead by a sibling?
+            if ent is not None and ent[0] == argkey and not q.ready() and torch.equal(ent[1], W):
+                out = ent[2]
+            sibs = [] if (out is not None or q.ready()) else self._siblings_to_solve_with(acc, argkey, R)
+            del H
         self._H = None
         self._consumed = True
-        dead, perm, invperm, U, info, Kp = (sol[k] for k in ("dead", "perm", "invperm", "U", "info", "Kp"))
+        if out is None:
+            Ws = [W] + [g._weight_rows(row_range) for g in sibs]
+            outs = _solve_rows(Ws, sol, qcfg, blocksize, groupsize, actorder, static_groups, self.layer.weight.data.dtype,
+                               preset=(q.scale, q.zero) if q.ready() else None)
+            out = outs[0]
+            for g, wsrc, o in zip(sibs, Ws[1:], outs[1:]):
+                acc.spec[id(g)] = (argkey, wsrc.clone(), o)
+        info, perm = sol["info"], sol["perm"]
 
-        f32 = dict(device=dev, dtype=torch.float32)
-        with _prof("prologue"):
-            W32 = torch.empty((R, K), **f32)
-            _lib.check(lib.gptq_b200_weights_prepare(W.data_ptr(), _lib.dt(W), R, K, W.stride(0), dead.data_ptr(),
-                                                     W32.data_ptr(), K, st), "weights_prepare")
-            _dbg("weights_prepare")
-            grouped = groupsize != -1
-            ng = 1 if not grouped else (K + groupsize - 1) // groupsize
-            gscale = gzero = None
-            if static_groups and grouped:               # gptq.py:157-163, on the un-permuted, un-updated W
-                gscale, gzero = find_params_groups(W32, maxq, q.sym, q.mse, q.norm, q.grid, q.maxshrink, groupsize)
-                _dbg("find_params_groups")
-            if actorder:                                # gptq.py:168
-                Wp = torch.empty_like(W32)
-                _lib.check(lib.gptq_b200_permute_cols(W32.data_ptr(), R, K, K, perm.data_ptr(), Wp.data_ptr(), K, st),
-                           "permute_cols")
-                del W32
-            else:
-                Wp = W32
-
-        if not q.ready():                               # gptq.py:181-185
-            q.find_params(Wp)
-
-        if not grouped:
-            mode = 0
-            scale = q.scale.to(dev).reshape(R, 1).float().contiguous().clone()
-            zero = q.zero.to(dev).reshape(R, 1).float().contiguous().clone()
-            gidx = None
-        elif static_groups:
-            mode = 0
-            scale, zero = gscale, gzero
-            cols = perm.long() if actorder else torch.arange(K, device=dev)
-            gidx = (cols // groupsize).to(torch.int32).contiguous()
-        else:
-            mode = 1
-            scale = torch.zeros((R, ng), **f32)
-            zero = torch.zeros((R, ng), **f32)
-            gidx = (torch.arange(K, device=dev) // groupsize).to(torch.int32).contiguous()
-
-        Q = torch.empty((R, K), **f32)
-        codes = torch.empty((R, K), device=dev, dtype=torch.uint8)
-        loss = torch.zeros(1, device=dev, dtype=torch.float64)
-        nws = lib.gptq_b200_colloop_workspace_bytes(R, K, blocksize)
-        ws = torch.empty(max(nws, 16), device=dev, dtype=torch.uint8)
-        # algorithmic bytes of the column loop: W fp16 in, U upper fp32, Q fp16 + codes out
-        with _prof("colloop", 2.0 * R * K + 2.0 * K * (K + 1) + 2.0 * R * K + R * K + 8.0 * R * ng):
-            _lib.check(lib.gptq_b200_colloop(Wp.data_ptr(), R, K, K, U.data_ptr(), Kp, blocksize, groupsize, mode,
-                                             _lib.ptr(gidx), scale.data_ptr(), zero.data_ptr(), ng, maxq, int(q.sym),
-                                             int(q.mse), float(q.norm), int(q.grid), float(q.maxshrink), Q.data_ptr(), K,
-                                             codes.data_ptr(), K, loss.data_ptr(), ws.data_ptr(), nws, st), "colloop")
-
-        # gptq.py:300-305: un-permute and write back in the layer's dtype
-        wdtype = self.layer.weight.data.dtype
-        Wout = torch.empty((R, K), device=dev, dtype=wdtype)
-        codes_out = torch.empty((R, K), device=dev, dtype=torch.uint8)
-        with _prof("epilogue", 4.0 * R * K + R * K + 2.0 * R * K + R * K):
-            _lib.check(lib.gptq_b200_finalize(Q.data_ptr(), K, codes.data_ptr(), K, R, K, _lib.ptr(invperm), Wout.data_ptr(),
-                                              _lib.dt(Wout), K, codes_out.data_ptr(), K, st), "finalize")
-
-        # Everything that does not need a host value is queued BEFORE the one synchronisation point, so the device is not
-        # left idle while Python post-processes: outputs in the caller's column order, the quantizer state the reference
-        # leaves behind, and ONE small record (info, sharing flag, loss) that is read back with a single copy.
-        if gidx is None:
-            g_idx_out = torch.zeros(K, device=dev, dtype=torch.int32)
-        else:
-            g_idx_out = gidx[invperm.long()].contiguous() if actorder else gidx
-        q_after, q_scale, q_zero = q, None, None
-        if grouped:
-            # what `self.quantizer` holds after the run: the parameters of the group of the LAST processed
-            # column -- gidx is in processing order, so that group is gidx[K-1]
-            if static_groups:
-                q_after = copy.deepcopy(q)             # the reference swaps in groups[...] (a deepcopy), gptq.py:260
-            if static_groups and actorder:
-                last = gidx[K - 1:K].long()
-                q_scale, q_zero = scale.index_select(1, last), zero.index_select(1, last)
-            else:
-                q_scale, q_zero = scale[:, ng - 1:ng].clone(), zero[:, ng - 1:ng].clone()
-        rec = torch.cat([info.to(torch.float64), (flag if flag is not None else info.new_zeros(1)).to(torch.float64), loss])
-        # gptq.py:292 calls torch.cuda.synchronize(); everything here was issued on the current stream, so reading the
-        # record back (a stream-ordered blocking copy) is the synchronisation -- a device-wide sync would also wait for
-        # unrelated streams (e.g. the caller's H2D prefetch)
-        rec = rec.cpu()
+        # Everything that does not need a host value was queued BEFORE this one synchronisation point; ONE small record
+        # (info, sharing flag, loss) is read back with a single copy.  gptq.py:292 calls torch.cuda.synchronize();
+        # everything here was issued on the current stream, so the stream-ordered blocking copy is the synchronisation --
+        # a device-wide sync would also wait for unrelated streams (e.g. the caller's H2D prefetch).
+        rec = torch.cat([info.to(torch.float64), (flag if flag is not None else info.new_zeros(1)).to(torch.float64),
+                         out["loss"]]).cpu()
         self._release()
         if rec[1] != 0:
             raise RuntimeError("GPTQ: a batch assumed identical for linears sharing one Hessian accumulator differed "
@@ -600,6 +704,7 @@ class GPTQ:
         print('time %.2f' % (time.time() - tick))
         print('error', self.error)
 
+        Wout = out["Wout"]
         if row_range is None:
             if isinstance(self.layer, _Conv1D):
                 Wfull = Wout.t()
@@ -607,13 +712,21 @@ class GPTQ:
                 Wfull = Wout
             self.layer.weight.data = Wfull.reshape(self.layer.weight.shape)
         self.Wq = Wout                                  # [rows(shard), K] dequantised weights in the layer dtype
-        self.codes = codes_out
-        self.scales = scale
-        self.zeros = zero
+        self.codes = out["codes"]
+        self.scales = out["scale"]
+        self.zeros = out["zero"]
         self.perm = perm
-        self.g_idx = g_idx_out
-        if q_scale is not None:
-            q_after.scale, q_after.zero = q_scale, q_zero
+        self.g_idx = out["g_idx"]
+        # quantizer state the reference leaves behind: find_params on the full rows (gptq.py:181-185, quant.py:39,105-109) ...
+        if out["full_scale"] is not None:
+            q.maxq = torch.full((), qcfg[0], dtype=q.maxq.dtype, device=dev) if q.maxq.device != dev else q.maxq
+            q.scale, q.zero = out["full_scale"], out["full_zero"]
+        # ... then, with groups, the parameters of the group of the LAST processed column
+        q_after = q
+        if out["q_scale"] is not None:
+            if static_groups:
+                q_after = copy.deepcopy(q)             # the reference swaps in groups[...] (a deepcopy), gptq.py:260
+            q_after.scale, q_after.zero = out["q_scale"], out["q_zero"]
         self.quantizer = q_after
         if DEBUG:
             print(torch.sum((self.layer(self.inp1) - self.out1) ** 2))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GPTQ_B200_ABI_VERSION 1
+#define GPTQ_B200_ABI_VERSION 2
 
 enum { GPTQ_B200_F16 = 0, GPTQ_B200_BF16 = 1, GPTQ_B200_F32 = 2 };
 
@@ -138,14 +138,15 @@ int gptq_b200_quantize(const float* x, int R, int C, int64_t ldx, const float* s
  *               written to scale/zero.
  *     Q      [R,K] fp32 dequantised weights, permuted order.
  *     codes  [R,K] uint8 integer codes, permuted order (trits: 0/1/2).
- *     loss   device double: sum(Losses) as printed at gptq.py:294.
+ *     row_loss [R] fp32, overwritten: row_loss[r] = sum_k Losses[r,k] (gptq.py:267,274); the scalar printed at
+ *            gptq.py:294 is its sum (reduced by the caller, per linear, in double).
  * ------------------------------------------------------------------------------------------ */
 size_t gptq_b200_colloop_workspace_bytes(int R, int K, int blocksize);
 int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const float* U, int64_t ldu,
                       int blocksize, int groupsize, int mode, const int32_t* gidx,
                       float* scale, float* zero, int ngroups, int maxq, int sym, int mse,
                       float norm, int grid, float maxshrink,
-                      float* Q, int64_t ldq, uint8_t* codes, int64_t ldc, double* loss,
+                      float* Q, int64_t ldq, uint8_t* codes, int64_t ldc, float* row_loss,
                       void* ws, size_t ws_bytes, void* stream);
 /* Device self-test of the column loop's division: counts pairs (a,b) out of n pseudo-random ones
  * for which the hoisted-reciprocal quotient differs from div.rn.f32 (must be 0).  *mismatches is a

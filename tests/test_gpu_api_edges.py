@@ -325,3 +325,57 @@ def test_non_finite_activations_raise_linalgerror_instead_of_faulting():
     g2 = _gptq(nn.Linear(K, R, bias=False).half().to(DEV))
     g2.add_batch(_acts(300, K, 1).to(DEV), None)
     _quiet(g2.fasterquant, actorder=True, groupsize=128)
+
+
+def test_siblings_are_solved_in_one_column_loop_and_match_individual_solves():
+    """q/k/v-style linears: the first fasterquant solves the siblings' rows in the same column loop; each sibling's own
+    call then only publishes.  Results must equal the ungrouped run (same codes up to rounding ties, same error)."""
+    from gptq_b200 import _lib
+    import gptq_b200.gptq as G
+    K, R = 256, 40
+    Ws, lins = _three_linears(K, R)
+    X = [_acts(300, K, i).to(DEV) for i in range(2)]
+
+    def run(group):
+        G.GROUP_SIBLINGS = group
+        try:
+            _, ls = _three_linears(K, R)
+            gs = [_gptq(l) for l in ls]
+            for x in X:
+                for g in gs:
+                    g.add_batch(x, None)
+            counts = []
+            for g in gs:
+                n0 = _lib.launch_count()
+                _quiet(g.fasterquant, groupsize=64, actorder=True, static_groups=True)
+                counts.append(_lib.launch_count() - n0)
+            return gs, ls, counts
+        finally:
+            G.GROUP_SIBLINGS = True
+    ga, la, ca = run(True)
+    gb, lb, cb = run(False)
+    assert ca[1] < cb[1] // 4 and ca[2] < cb[2] // 4                # siblings only publish
+    for a, b, x, y in zip(ga, gb, la, lb):
+        assert O.code_agreement(a.codes.cpu(), b.codes.cpu()) >= 0.999
+        assert abs(a.error - b.error) <= 1e-3 * abs(b.error)
+        assert torch.equal(a.scales, b.scales) and torch.equal(a.zeros, b.zeros)
+        assert torch.equal(a.quantizer.scale, b.quantizer.scale)
+        assert (x.weight.data == y.weight.data).float().mean() >= 0.999
+    # a sibling whose weights changed after it was solved ahead is solved again with the new weights
+    _, ls = _three_linears(K, R)
+    gs = [_gptq(l) for l in ls]
+    for x in X:
+        for g in gs:
+            g.add_batch(x, None)
+    _quiet(gs[0].fasterquant, groupsize=64)
+    ls[1].weight.data = (ls[1].weight.data * 1.5)
+    st = O.HessianState(K)
+    for x in X:
+        O.add_batch(st, x.cpu())
+    _quiet(gs[1].fasterquant, groupsize=64)
+    ref = O.fasterquant((Ws[1].float() * 1.5).half(), st.H, O.QParams(bits=4), groupsize=64)
+    assert O.code_agreement(gs[1].codes.cpu(), ref.codes) >= 0.999
+    # ... and one called with other arguments as well
+    _quiet(gs[2].fasterquant, groupsize=-1)
+    ref = O.fasterquant(Ws[2], st.H, O.QParams(bits=4), groupsize=-1)
+    assert O.code_agreement(gs[2].codes.cpu(), ref.codes) >= 0.999

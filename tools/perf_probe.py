@@ -88,7 +88,7 @@ def probe_colloop(R, K, gs=128):
     gidx = (torch.arange(K, device=DEV) // gs).to(torch.int32)
     Qo = torch.empty(R, K, device=DEV)
     codes = torch.empty(R, K, dtype=torch.uint8, device=DEV)
-    loss = torch.zeros(1, dtype=torch.float64, device=DEV)
+    loss = torch.zeros(R, dtype=torch.float32, device=DEV)
     n = lib.gptq_b200_colloop_workspace_bytes(R, K, 128)
     ws = torch.empty(n, dtype=torch.uint8, device=DEV)
     W = torch.empty_like(W0)
