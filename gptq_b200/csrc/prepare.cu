@@ -148,6 +148,37 @@ stage_vec_kernel(const uint4* __restrict__ src, int64_t tokens, int kv, int64_t 
     }
 }
 
+// Dense case (no padding on either side): one flat grid-stride pass, 4 independent 16-byte loads per thread in flight.
+__global__ void __launch_bounds__(256)
+copy_flat_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t nvec) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < nvec; i += stride) dst[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256)
+compare_flat_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, int64_t nvec, int32_t* __restrict__ flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool diff = false;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        const uint4 x0 = a[i], x1 = a[i + stride], x2 = a[i + 2 * stride], x3 = a[i + 3 * stride];
+        const uint4 y0 = b[i], y1 = b[i + stride], y2 = b[i + 2 * stride], y3 = b[i + 3 * stride];
+        diff |= (x0.x != y0.x) | (x0.y != y0.y) | (x0.z != y0.z) | (x0.w != y0.w) | (x1.x != y1.x) | (x1.y != y1.y) |
+                (x1.z != y1.z) | (x1.w != y1.w) | (x2.x != y2.x) | (x2.y != y2.y) | (x2.z != y2.z) | (x2.w != y2.w) |
+                (x3.x != y3.x) | (x3.y != y3.y) | (x3.z != y3.z) | (x3.w != y3.w);
+    }
+    for (; i < nvec; i += stride) {
+        const uint4 x = a[i], y = b[i];
+        diff |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+    }
+    if (__syncthreads_or(diff) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
 // ------------------------------------------------------------------ exact (bitwise) comparison of two 16-bit batches
 // flag |= 1 when any element differs.  Used to verify that a batch handed to a second GPTQ object is the very
 // batch already staged by the first one before their Hessian accumulators are shared (gptq.py:38-65 computes
@@ -294,6 +325,13 @@ extern "C" int gptq_b200_stage_input(const void* src, int dtype, int64_t tokens,
         (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
         const int kv = K / 8;
         const int64_t ldd_v = ld_dst / 8;
+        if (ld_src == K && ld_dst == K) {
+            const int64_t nvec = tokens * kv;
+            int64_t nb = (nvec + 1023) / 1024; if (nb > num_sms() * 8) nb = num_sms() * 8;
+            copy_flat_kernel<<<(int)nb, 256, 0, st>>>((const uint4*)src, (uint4*)dst, nvec);
+            GQ_LAUNCHED();
+            return 0;
+        }
         int gx = cdiv(ldd_v, 256); if (gx > 4) gx = 4;
         dim3 g(gx, (unsigned)(tokens > 1184 ? 1184 : tokens));
         stage_vec_kernel<<<g, 256, 0, st>>>((const uint4*)src, tokens, kv, ld_src / 8, (uint4*)dst, ldd_v);
@@ -314,6 +352,13 @@ extern "C" int gptq_b200_compare_rows(const void* a, int64_t lda, const void* b,
     if (tokens == 0) return 0;
     const int vec = (K % 8 == 0) && (lda % 8 == 0) && (ldb % 8 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    if (vec && lda == K && ldb == K) {
+        const int64_t nvec = tokens * (K / 8);
+        int64_t nb = (nvec + 1023) / 1024; if (nb > num_sms() * 8) nb = num_sms() * 8;
+        compare_flat_kernel<<<(int)nb, 256, 0, as_stream(stream)>>>((const uint4*)a, (const uint4*)b, nvec, flag);
+        GQ_LAUNCHED();
+        return 0;
+    }
     const int per_row = vec ? K / 8 : K;
     dim3 g(cdiv(per_row, 256) > 8 ? 8 : cdiv(per_row, 256), (unsigned)(tokens > 2048 ? 2048 : tokens));
     compare_rows_kernel<<<g, 256, 0, as_stream(stream)>>>((const uint16_t*)a, lda, (const uint16_t*)b, ldb, tokens, K, vec, flag);

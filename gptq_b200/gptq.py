@@ -59,6 +59,19 @@ SHARE_VERIFY = os.environ.get("GPTQ_B200_SHARE_VERIFY", "1") == "1"
 # Linears that share a Hessian and are quantized with the same arguments are solved in ONE column loop (their rows
 # stacked): the loop is latency-bound, so three 4096-row linears cost little more than one.
 GROUP_SIBLINGS = os.environ.get("GPTQ_B200_GROUP_SIBLINGS", "1") == "1"
+# Opt-in: the syrk of a full staging slab runs on a side stream while the NEXT samples are being staged (and verified)
+# into a second slab on the caller's stream (the copies are HBM-bound, the syrk tensor-bound, their CTAs fit on an SM
+# together).  Measured on the power-capped B200 box: the 2.6 ms of hidden staging per layer are given back by lower
+# clocks in the kernels that follow (step time 112.3 ms either way), so the default stays single-stream.
+OVERLAP_SYRK = os.environ.get("GPTQ_B200_OVERLAP_SYRK", "0") == "1"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    st = _SIDE_STREAMS.get(dev)
+    if st is None:
+        st = _SIDE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return st
 
 
 # Optional per-call device timing: set ``gptq_b200.gptq.PROFILE = []`` and every C-ABI hot call appends
@@ -107,11 +120,12 @@ def syrk_issued_flops(K: int, tokens: int) -> float:
     return 2.0 * tiles * 128 * 256 * tokens
 
 
+_ACT_DTYPES = (torch.float16, torch.bfloat16, torch.float32)
 _JOINABLE = {}            # (device, batch identity) -> weakref(_Accumulator that has absorbed exactly that one batch)
 
 
 def _batch_key(x):
-    return (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype)
+    return (x.data_ptr(), x.shape, x.stride(), x.dtype)
 
 
 class _Accumulator:
@@ -122,7 +136,11 @@ class _Accumulator:
     def __init__(self, K, dev):
         self.K, self.dev = K, dev
         self.S = None                  # [K,K] fp32, tiles touching the lower triangle valid
-        self.stage = None              # [cap_tokens, roundup(K,8)] staging slab
+        self.stage = None              # [cap_tokens, roundup(K,8)] staging slab being filled
+        self.stage_other = None        # the second slab (being consumed by a syrk on the side stream, or idle)
+        self.stage_busy = None         # event: the syrk reading `stage` (from its previous turn) has finished
+        self.other_busy = None
+        self.syrk_ev = None            # event: the last syrk launched on the side stream has finished
         self.staged = 0
         self.ws = None
         self.count = 0                 # samples absorbed (the reference's nsamples)
@@ -135,6 +153,7 @@ class _Accumulator:
         self.last_tokens = 0
         self.last_in_slab = False      # the most recent batch sits contiguously at the end of the slab
         self.last = None               # (view of the last batch, count at that time) for GPTQ.input
+        self.last_slab = None
         self.flag = None               # device int32, set by compare_rows when a shared batch was NOT identical
         self.reduced = False           # dist.allreduce_hessian already summed S over the ranks
         self.sealed = False
@@ -166,6 +185,7 @@ class _Accumulator:
         if x.dtype == torch.float32:
             # fp32 activations: exact fp32 CUDA-core path (the tensor path takes 16-bit operands)
             self.flush()
+            self.wait_syrk()
             xc = x.contiguous()
             _lib.check(lib.gptq_b200_syrk_accum_simt(xc.data_ptr(), _lib.F32, tokens, K, xc.stride(0), self.S.data_ptr(), K,
                                                      1.0, 1.0, _lib.stream()), "syrk_accum_simt")
@@ -176,12 +196,27 @@ class _Accumulator:
             x = x.contiguous()
         if self.stage is None or self.stage.dtype != x.dtype:
             self.flush()
+            self.wait_syrk()
             cap = max(tokens, 1) * max(STAGE_SAMPLES, 1)
             self.stage = torch.empty((cap, _round_up(K, 8)), device=self.dev, dtype=x.dtype)
+            self.stage_other = self.stage_busy = self.other_busy = None
         cap = self.stage.shape[0]
         if tokens <= cap and self.staged + tokens > cap:
             self.flush()                                   # keep a batch contiguous in the slab
         in_slab = tokens <= cap
+        if in_slab:                                        # the common case: no slicing, plain pointer arithmetic
+            st_ = self.stage
+            ld = st_.stride(0)
+            rc = lib.gptq_b200_stage_input(x.data_ptr(), _lib.dt(x), tokens, K, x.stride(0),
+                                           st_.data_ptr() + self.staged * ld * st_.element_size(), ld,
+                                           torch.cuda.current_stream().cuda_stream)
+            if rc:
+                _lib.check(rc, "stage_input")
+            self.last = (self.staged, tokens, self.count)  # resolved lazily by GPTQ.input
+            self.last_slab = st_
+            self.staged += tokens
+            self.last_in_slab = True
+            return
         done = 0
         while done < tokens:
             if self.staged == cap:
@@ -194,21 +229,33 @@ class _Accumulator:
             self.last = (dst[:, :K], self.count)
             self.staged += n
             done += n
-        self.last_in_slab = in_slab
+        self.last_in_slab = False
 
     def verify(self, x):
-        """Device-side proof that `x` is bit-identical to the batch staged last (result read at fasterquant's sync)."""
+        """Device-side proof that `x` is bit-identical to the batch staged last (result read at fasterquant's sync).
+        Runs once per sample and sibling: no tensor slicing, plain pointer arithmetic."""
         if not SHARE_VERIFY:
             return
         if self.flag is None:
             self.flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
-        ref = self.stage[self.staged - self.last_tokens:self.staged]
         if x.stride(-1) != 1:
             x = x.contiguous()
-        _lib.check(_lib.load().gptq_b200_compare_rows(x.data_ptr(), x.stride(0), ref.data_ptr(), ref.stride(0), x.shape[0],
-                                                      self.K, self.flag.data_ptr(), _lib.stream()), "compare_rows")
+        st = self.stage
+        ld = st.stride(0)
+        ref_ptr = st.data_ptr() + (self.staged - self.last_tokens) * ld * st.element_size()
+        rc = _lib.load().gptq_b200_compare_rows(x.data_ptr(), x.stride(0), ref_ptr, ld, x.shape[0], self.K,
+                                                self.flag.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _lib.check(rc, "compare_rows")
+
+    def wait_syrk(self):
+        """Make the current stream wait for the accumulation launched on the side stream."""
+        if self.syrk_ev is not None:
+            torch.cuda.current_stream(self.dev).wait_event(self.syrk_ev)
 
     def flush(self):
+        """Fold the staged tokens into S.  With OVERLAP_SYRK the kernel goes to the side stream and staging continues in
+        the other slab; S is valid on the caller's stream only after wait_syrk()."""
         self.last_in_slab = False
         if self.stage is None or self.staged == 0:
             return
@@ -216,11 +263,38 @@ class _Accumulator:
         K = self.K
         need = lib.gptq_b200_syrk_workspace_bytes(K, self.staged)
         if need and (self.ws is None or self.ws.numel() < need):
+            self.wait_syrk()                               # the old workspace may still be in use
             self.ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
-        with _prof("syrk", syrk_issued_flops(K, self.staged), (K, self.staged)):
-            _lib.check(lib.gptq_b200_syrk_accum(self.stage.data_ptr(), _lib.dt(self.stage), self.staged, K,
-                                                self.stage.stride(0), self.S.data_ptr(), K, 1.0, 1.0, CHUNK_TOKENS,
-                                                _lib.ptr(self.ws) if need else 0, need, _lib.stream()), "syrk_accum")
+
+        def launch():
+            with _prof("syrk", syrk_issued_flops(K, self.staged), (K, self.staged)):
+                _lib.check(lib.gptq_b200_syrk_accum(self.stage.data_ptr(), _lib.dt(self.stage), self.staged, K,
+                                                    self.stage.stride(0), self.S.data_ptr(), K, 1.0, 1.0, CHUNK_TOKENS,
+                                                    _lib.ptr(self.ws) if need else 0, need, _lib.stream()), "syrk_accum")
+        if not OVERLAP_SYRK:
+            launch()
+            self.staged = 0
+            return
+        main = torch.cuda.current_stream(self.dev)
+        side = _side_stream(self.dev)
+        for t in (self.stage, self.S, self.ws):            # allocated on the caller's stream, used on the side stream
+            if t is not None:
+                t.record_stream(side)
+        ready = torch.cuda.Event()
+        ready.record(main)                                 # the window is staged (and S initialised)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            launch()
+            done = torch.cuda.Event()
+            done.record(side)
+        self.syrk_ev = done
+        # continue staging in the other slab, once the syrk that last read it has finished
+        self.stage, self.stage_other = self.stage_other, self.stage
+        self.stage_busy, self.other_busy = self.other_busy, done
+        if self.stage is None:
+            self.stage = torch.empty_like(self.stage_other)
+        elif self.stage_busy is not None:
+            main.wait_event(self.stage_busy)
         self.staged = 0
 
     def _unregister(self):
@@ -242,6 +316,7 @@ class _Accumulator:
         if self.S is None:
             return torch.zeros((self.K, self.K), device=self.dev, dtype=torch.float32)
         self.flush()
+        self.wait_syrk()
         H = self.S.clone()
         _lib.check(_lib.load().gptq_b200_symmetrize(H.data_ptr(), self.K, self.K, _lib.stream()), "symmetrize")
         if n > 0:
@@ -260,6 +335,7 @@ class _Accumulator:
         if self.S is None:
             self.S = torch.zeros((K, K), device=self.dev, dtype=torch.float32)
         self.flush()
+        self.wait_syrk()
         self._unregister()
         H = self.S
         _lib.check(lib.gptq_b200_symmetrize(H.data_ptr(), K, K, _lib.stream()), "symmetrize")
@@ -268,7 +344,7 @@ class _Accumulator:
         self.dead = torch.empty(K, device=self.dev, dtype=torch.uint8)
         _lib.check(lib.gptq_b200_dead_columns(H.data_ptr(), K, K, self.dead.data_ptr(), _lib.stream()), "dead_columns")
         self.H, self.S, self.n_final, self.sealed = H, None, n, True
-        self.stage = self.ws = self.ref = self.last = None
+        self.stage = self.stage_other = self.ws = self.ref = self.last = self.last_slab = None
         return H
 
 
@@ -442,6 +518,7 @@ class GPTQ:
         self.columns = W.shape[1]
         self.nsamples = 0
         self.quantizer = None
+        self._is_linear = isinstance(self.layer, nn.Linear) or isinstance(self.layer, _Conv1D)
         self._acc = None               # _Accumulator (allocated with the first batch; may be shared, see SHARE_H)
         self._H = None                 # materialised (2/n)*S, full symmetric, or a user-provided H
         self._consumed = False
@@ -451,20 +528,21 @@ class GPTQ:
         if DEBUG:
             self.inp1 = inp
             self.out1 = out
-        _lib.require_cuda(inp, "GPTQ.add_batch: inp")
-        if len(inp.shape) == 2:
+        if not inp.is_cuda:
+            _lib.require_cuda(inp, "GPTQ.add_batch: inp")
+        if inp.dim() == 2:
             inp = inp.unsqueeze(0)
         tmp = inp.shape[0]
-        if isinstance(self.layer, nn.Linear) or isinstance(self.layer, _Conv1D):
-            if len(inp.shape) == 3:
+        if self._is_linear:
+            if inp.dim() == 3:
                 inp = inp.reshape((-1, inp.shape[-1]))            # [tokens, K]; the reference transposes, we don't need to
-        if isinstance(self.layer, nn.Conv2d):
+        elif isinstance(self.layer, nn.Conv2d):
             unfold = nn.Unfold(self.layer.kernel_size, dilation=self.layer.dilation, padding=self.layer.padding,
                                stride=self.layer.stride)
             inp = unfold(inp).permute([1, 0, 2]).flatten(1).t()   # [tokens, K]
         if inp.shape[-1] != self.columns:
             raise ValueError(f"add_batch: expected {self.columns} input features, got {inp.shape[-1]}")
-        if inp.dtype not in (torch.float16, torch.bfloat16, torch.float32):
+        if inp.dtype not in _ACT_DTYPES:
             raise TypeError(f"unsupported dtype {inp.dtype}")
         if self._consumed:
             raise RuntimeError("add_batch: H was already consumed by fasterquant or freed")
@@ -512,6 +590,7 @@ class GPTQ:
             raise RuntimeError("GPTQ: linears sharing a Hessian accumulator received different batches and the common "
                                "state can no longer be separated; set GPTQ_B200_SHARE_H=0")
         new = _Accumulator(acc.K, acc.dev)
+        acc.wait_syrk()
         new.S = acc.S.clone() if acc.S is not None else None
         if acc.stage is not None:
             new.stage = torch.empty_like(acc.stage)
@@ -571,7 +650,12 @@ class GPTQ:
         acc = self._acc
         if acc is None or acc.last is None:
             raise AttributeError("input")
-        x, n = acc.last
+        if len(acc.last) == 3:                              # (row offset, tokens, count) in the slab staged last
+            off, tokens, n = acc.last
+            slab = acc.last_slab
+            x = slab[off:off + tokens, :acc.K]
+        else:
+            x, n = acc.last
         return math.sqrt(2 / n) * x.float().mean(0)
 
     def raw_accumulator(self):
@@ -582,6 +666,7 @@ class GPTQ:
         if acc.S is None:
             acc.S = torch.zeros((self.columns, self.columns), device=self.dev, dtype=torch.float32)
         acc.flush()
+        acc.wait_syrk()
         self._H = None
         return acc.S
 

@@ -379,3 +379,23 @@ def test_siblings_are_solved_in_one_column_loop_and_match_individual_solves():
     _quiet(gs[2].fasterquant, groupsize=-1)
     ref = O.fasterquant(Ws[2], st.H, O.QParams(bits=4), groupsize=-1)
     assert O.code_agreement(gs[2].codes.cpu(), ref.codes) >= 0.999
+
+
+def test_overlapped_syrk_on_side_stream_gives_the_same_hessian():
+    """GPTQ_B200_OVERLAP_SYRK: the accumulation runs on a side stream with two staging slabs; same H, bit for bit."""
+    import gptq_b200.gptq as G
+    K, R = 256, 16
+    X = [_acts(300, K, i).to(DEV) for i in range(40)]               # > 2 slabs of 16 samples
+    Hs = []
+    for flag in (False, True):
+        G.OVERLAP_SYRK = flag
+        try:
+            g = _gptq(nn.Linear(K, R, bias=False).half().to(DEV))
+            for x in X:
+                g.add_batch(x, None)
+            Hs.append(g.H.clone())
+            _quiet(g.fasterquant, groupsize=128)
+        finally:
+            G.OVERLAP_SYRK = False
+    torch.cuda.synchronize()
+    assert torch.equal(Hs[0], Hs[1])
