@@ -471,8 +471,9 @@ def run_ours(args):
                "d2h_bytes_per_step": d2h * world, "ms_per_step": ems / e_steps, "steps": e_steps}
         del acts_h, weights_h
     except Exception as ex:  # pinned allocation can fail on small hosts; report instead of hiding
-        import traceback
-        traceback.print_exc(file=sys.stderr)
+        if not args.no_e2e:
+            import traceback
+            traceback.print_exc(file=sys.stderr)
         e2e = {"value": None, "unit": "Mweights/s", "error": repr(ex)}
 
     if rank == 0:

@@ -704,7 +704,8 @@ class GPTQ:
             g = ref()
             if g is None or g is self or g._acc is not acc or g._consumed or g._H is not None or id(g) in acc.spec:
                 continue
-            if g.nsamples != self.nsamples or g.rows != self.rows or g.columns != self.columns:
+            # (after dist.allreduce_hessian the siblings pick up the global sample count at their own turn)
+            if (g.nsamples != self.nsamples and not acc.reduced) or g.rows != self.rows or g.columns != self.columns:
                 continue
             if type(g.layer) is not type(self.layer) or g.layer.weight.dtype != self.layer.weight.dtype:
                 continue
