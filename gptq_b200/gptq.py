@@ -207,9 +207,9 @@ class _Accumulator:
         if in_slab:                                        # the common case: no slicing, plain pointer arithmetic
             st_ = self.stage
             ld = st_.stride(0)
-            rc = lib.gptq_b200_stage_input(x.data_ptr(), _lib.dt(x), tokens, K, x.stride(0),
-                                           st_.data_ptr() + self.staged * ld * st_.element_size(), ld,
-                                           torch.cuda.current_stream().cuda_stream)
+            rc = 0 if tokens == 0 else lib.gptq_b200_stage_input(
+                x.data_ptr(), _lib.dt(x), tokens, K, x.stride(0), st_.data_ptr() + self.staged * ld * st_.element_size(), ld,
+                torch.cuda.current_stream().cuda_stream)
             if rc:
                 _lib.check(rc, "stage_input")
             self.last = (self.staged, tokens, self.count)  # resolved lazily by GPTQ.input
