@@ -168,6 +168,288 @@ chol_diag_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict_
         }
 }
 
+// ------------------------------------------------------------------ diagonal block, fused factor + inverse
+// chol_diag_kernel spends 256 barrier-separated steps: 128 for the backward Cholesky A = R R^T and 128 for X = R^-1.
+// The inverse can ride along with the factorisation.  With T = diag(R) * R^-1 (so V = R^-1 has rows V[i] = T[i] / R[i][i]):
+//     T[i][:] = e_i - sum_{k > i} R[i][k] * V[k][:]
+// and row k of V is final as soon as the steps k' > k are done -- the same moment column k of R is.  So step k
+// (k = 127 .. 0) publishes column k of R AND row k of T, and every thread applies two rank-1 updates to its register tiles:
+//     A[i][c] -= R[i][k] R[c][k]     (i, c < k)            the Schur update of the factorisation
+//     T[i][c] -= R[i][k] V[k][c]     (i < k, c >= k)       the elimination of the inverse
+// The two updates touch complementary column ranges, i.e. one full 8x8 tile of FMAs per thread and step -- the same
+// arithmetic as before, in 128 barrier steps instead of 256.
+template <int NB>
+__device__ __forceinline__ void diag3_publish(float (&r)[8][8], float (&t)[8][8], float* colb, float* trow, float* rd,
+                                              int32_t* info, int base_index, int kt, int tx, int ty, int warp) {
+    const int k = NB * 16 + kt;
+    if (warp == (kt >> 1)) {                                   // the warp holding column k of A (warp-uniform)
+        const float v = __shfl_sync(0xffffffffu, r[NB][NB], ((kt & 1) << 4) | kt);       // pivot (k,k)
+        const float rinv = inv_sqrt(v);
+        if (tx == kt) {
+            if (ty == kt) {
+                if (!(v > 0.f)) atomicCAS(info, 0, base_index + k + 1);
+                rd[k] = rinv;
+            }
+#pragma unroll
+            for (int a = 0; a <= NB; ++a) {
+                const int row = a * 16 + ty;
+                float c = r[a][NB] * rinv;                     // row == k: v * rsqrt(v) = sqrt(v)
+                if (row > k) c = 0.f;
+                colb[row] = c;
+            }
+        }
+    }
+    if (ty == kt) {                                            // the owners of row k of T (all warps): columns b*16+tx
+#pragma unroll
+        for (int b = NB; b < 8; ++b) trow[b * 16 + tx] = t[NB][b];
+    }
+}
+
+template <int KB>
+__device__ __forceinline__ void diag3_block(float (&r)[8][8], float (&t)[8][8], float* colb2, float* trow2, float* rd,
+                                            int32_t* info, int base_index, int tx, int ty, int warp) {
+#pragma unroll 1
+    for (int kt = 15; kt >= 0; --kt) {
+        const int k = KB * 16 + kt;
+        const float* colb = colb2 + (k & 1) * CB;
+        const float* trow = trow2 + (k & 1) * CB;
+        __syncthreads();                                       // column k of R, row k of T, rd[k] visible
+        float cr[KB + 1], cc[KB + 1], vr[8];
+        const float rinv = rd[k];
+#pragma unroll
+        for (int a = 0; a <= KB; ++a) cr[a] = colb[a * 16 + ty];
+#pragma unroll
+        for (int b = 0; b <= KB; ++b) cc[b] = colb[b * 16 + tx];
+#pragma unroll
+        for (int b = KB; b < 8; ++b) vr[b] = trow[b * 16 + tx] * rinv;           // V[k][c], c >= k (zero left of k)
+#pragma unroll
+        for (int a = 0; a <= KB; ++a) {
+            const bool rowact = (a < KB || ty < kt);                            // row < k
+#pragma unroll
+            for (int b = 0; b <= KB; ++b) {
+                const bool act = rowact && (b < KB || tx < kt);                 // col < k
+                if (act) r[a][b] = fmaf(-cr[a], cc[b], r[a][b]);
+            }
+#pragma unroll
+            for (int b = KB; b < 8; ++b) {
+                const bool act = rowact && (b > KB || tx >= kt);                // col >= k
+                if (act) t[a][b] = fmaf(-cr[a], vr[b], t[a][b]);
+            }
+        }
+        // publish step k-1 into the other buffers (their readers finished before the barrier above)
+        float* ncol = colb2 + ((k - 1) & 1) * CB;
+        float* nrow = trow2 + ((k - 1) & 1) * CB;
+        if (kt >= 1) diag3_publish<KB>(r, t, ncol, nrow, rd, info, base_index, kt - 1, tx, ty, warp);
+        else if (KB >= 1) diag3_publish<(KB >= 1 ? KB - 1 : 0)>(r, t, ncol, nrow, rd, info, base_index, 15, tx, ty, warp);
+    }
+}
+
+__global__ void __launch_bounds__(256, 1)
+chol_diag3_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict__ Dinv, int64_t ldd,
+                  int32_t* __restrict__ info, int base_index) {
+    __shared__ float colb[2 * CB];
+    __shared__ float trow[2 * CB];
+    __shared__ float rd[CB];                             // 1 / R[k][k]
+    const int tid = threadIdx.x;
+    const int tx = tid >> 4, ty = tid & 15, warp = tid >> 5;
+    ptx::pdl_launch_dependents();
+    ptx::pdl_wait();                                     // A_jj carries the preceding GEMM's Schur update
+
+    float r[8][8], t[8][8];                              // 64 independent loads per thread: one memory latency
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int row = a * 16 + ty, col = b * 16 + tx;
+            r[a][b] = (col >= row) ? __ldcg(&Ablk[(int64_t)row * lda + col]) : 0.f;   // L2: written by the kernel just before (PDL)
+            t[a][b] = (a == b && tx == ty) ? 1.f : 0.f;
+        }
+    for (int i = tid; i < 2 * CB; i += 256) { trow[i] = 0.f; }
+    __syncthreads();
+    diag3_publish<7>(r, t, colb + CB, trow + CB, rd, info, base_index, 15, tx, ty, warp);    // step 127 (odd -> buffer 1)
+    diag3_block<7>(r, t, colb, trow, rd, info, base_index, tx, ty, warp);
+    diag3_block<6>(r, t, colb, trow, rd, info, base_index, tx, ty, warp);
+    diag3_block<5>(r, t, colb, trow, rd, info, base_index, tx, ty, warp);
+    diag3_block<4>(r, t, colb, trow, rd, info, base_index, tx, ty, warp);
+    diag3_block<3>(r, t, colb, trow, rd, info, base_index, tx, ty, warp);
+    diag3_block<2>(r, t, colb, trow, rd, info, base_index, tx, ty, warp);
+    diag3_block<1>(r, t, colb, trow, rd, info, base_index, tx, ty, warp);
+    diag3_block<0>(r, t, colb, trow, rd, info, base_index, tx, ty, warp);
+    __syncthreads();                                     // every rd[] entry visible
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int row = a * 16 + ty;
+        const float ri = rd[row];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int col = b * 16 + tx;
+            Dinv[(int64_t)row * ldd + col] = (col >= row) ? t[a][b] * ri : 0.f;       // V = diag(R)^-1 T
+        }
+    }
+}
+
+// ------------------------------------------------------------------ fused kernel with a dedicated pivot warp
+// In chol_diag3_kernel the warp that owns the next column first applies its whole share of the rank-1 updates and only
+// then runs the pivot chain (shuffle, rsqrt, scale, store) -- with every other warp waiting at the barrier.  Here a ninth
+// warp owns no tile and does nothing but that chain: right after the barrier the owners bring their column up to date
+// (8 FMAs), hand it over raw through shared memory (named barrier 1: bar.arrive by the owner warp, bar.sync by the pivot
+// warp) and go on with their updates, while the pivot warp finishes and publishes the column for the next step.
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+// tile warps: send column (NB*16 + kt) of A, as it stands, to the pivot warp; publish row (NB*16 + kt) of T
+template <int NB>
+__device__ __forceinline__ void diag4_handover(float (&r)[8][8], float (&t)[8][8], float* rawc, float* trow, int kt, int tx,
+                                               int ty, int warp) {
+    if (warp == (kt >> 1)) {                                   // the warp holding that column (warp-uniform)
+        if (tx == kt) {
+#pragma unroll
+            for (int a = 0; a <= NB; ++a) rawc[a * 16 + ty] = r[a][NB];
+        }
+        __syncwarp();
+        named_arrive(1, 64);
+    }
+    if (ty == kt) {
+#pragma unroll
+        for (int b = NB; b < 8; ++b) trow[b * 16 + tx] = t[NB][b];
+    }
+}
+
+// pivot warp: raw column k -> scaled column of R in colb, 1/R[k][k] in rd
+__device__ __forceinline__ void diag4_pivot(const float* rawc, float* colb, float* rd, int32_t* info, int base_index, int k,
+                                            int lane) {
+    named_sync(1, 64);
+    const float v = rawc[k];
+    const float rinv = inv_sqrt(v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int row = q * 32 + lane;
+        if (row <= (k | 15)) {                                 // rows of the blocks the owners wrote
+            float c = rawc[row] * rinv;                        // row == k: v * rsqrt(v) = sqrt(v)
+            if (row > k) c = 0.f;
+            colb[row] = c;
+        }
+    }
+    if (lane == 0) {
+        rd[k] = rinv;
+        if (!(v > 0.f)) atomicCAS(info, 0, base_index + k + 1);
+    }
+}
+
+// One step's rank-1 updates with NO per-element predicates (the predicated form was issue-bound: ~250 instructions per
+// thread and step).  The masks are separable and almost free: the published column is already zero below its diagonal,
+// the published row of T is zero left of its diagonal, so only the diagonal entry itself has to be masked out of the two
+// multiplier vectors.  kt is uniform over the CTA, so the kt >= 1 / kt == 0 paths are plain branches over static code.
+template <int KB>
+__device__ __forceinline__ void diag4_block(float (&r)[8][8], float (&t)[8][8], float* colb2, float* trow2, float* rawc,
+                                            float* rd, int tx, int ty, int warp) {
+    constexpr int NBL = KB >= 1 ? KB - 1 : 0;                  // block of step k-1 when kt == 0
+#pragma unroll 1
+    for (int kt = 15; kt >= 0; --kt) {
+        const int k = KB * 16 + kt;
+        const float* colb = colb2 + (k & 1) * CB;
+        const float* trow = trow2 + (k & 1) * CB;
+        float* nrow = trow2 + ((k - 1) & 1) * CB;
+        __syncthreads();                                       // column k of R, row k of T, rd[k] visible
+        float cr[KB + 1], cc[KB + 1], vr[8];
+        const float rinv = rd[k];
+#pragma unroll
+        for (int a = 0; a <= KB; ++a) cr[a] = colb[a * 16 + ty];              // R[i][k]; 0 for i > k
+#pragma unroll
+        for (int b = 0; b <= KB; ++b) cc[b] = colb[b * 16 + tx];              // R[c][k]; 0 for c > k
+        cr[KB] = (ty < kt) ? cr[KB] : 0.f;                                     // drop i == k
+        cc[KB] = (tx < kt) ? cc[KB] : 0.f;                                     // drop c == k
+#pragma unroll
+        for (int b = KB; b < 8; ++b) vr[b] = trow[b * 16 + tx] * rinv;         // V[k][c]; 0 for c < k
+        if (kt >= 1) {
+            // part 1: column block KB of A and row block KB of T hold column / row k-1 -> hand them over first
+#pragma unroll
+            for (int a = 0; a <= KB; ++a) r[a][KB] = fmaf(-cr[a], cc[KB], r[a][KB]);
+#pragma unroll
+            for (int b = KB; b < 8; ++b) t[KB][b] = fmaf(-cr[KB], vr[b], t[KB][b]);
+            diag4_handover<KB>(r, t, rawc, nrow, kt - 1, tx, ty, warp);
+#pragma unroll
+            for (int a = 0; a <= KB; ++a) {
+#pragma unroll
+                for (int b = 0; b < KB; ++b) r[a][b] = fmaf(-cr[a], cc[b], r[a][b]);
+                if (a < KB) {
+#pragma unroll
+                    for (int b = KB; b < 8; ++b) t[a][b] = fmaf(-cr[a], vr[b], t[a][b]);
+                }
+            }
+        } else if (KB >= 1) {
+            // k = KB*16: rows and columns < k are exactly the blocks <= NBL
+#pragma unroll
+            for (int a = 0; a <= NBL; ++a) r[a][NBL] = fmaf(-cr[a], cc[NBL], r[a][NBL]);
+#pragma unroll
+            for (int b = KB; b < 8; ++b) t[NBL][b] = fmaf(-cr[NBL], vr[b], t[NBL][b]);
+            diag4_handover<NBL>(r, t, rawc, nrow, 15, tx, ty, warp);
+#pragma unroll
+            for (int a = 0; a <= NBL; ++a) {
+#pragma unroll
+                for (int b = 0; b < NBL; ++b) r[a][b] = fmaf(-cr[a], cc[b], r[a][b]);
+                if (a < NBL) {
+#pragma unroll
+                    for (int b = KB; b < 8; ++b) t[a][b] = fmaf(-cr[a], vr[b], t[a][b]);
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(288, 1)
+chol_diag4_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict__ Dinv, int64_t ldd,
+                  int32_t* __restrict__ info, int base_index) {
+    __shared__ float colb[2 * CB];
+    __shared__ float trow[2 * CB];
+    __shared__ float rawc[CB];
+    __shared__ float rd[CB];                             // 1 / R[k][k]
+    const int tid = threadIdx.x;
+    const int tx = (tid >> 4) & 15, ty = tid & 15, warp = tid >> 5, lane = tid & 31;
+    ptx::pdl_launch_dependents();
+    ptx::pdl_wait();                                     // A_jj carries the preceding GEMM's Schur update
+    if (warp == 8) {
+        // ===== pivot warp: column k-1 is published while the tile warps work on step k
+        diag4_pivot(rawc, colb + CB, rd, info, base_index, 127, lane);
+#pragma unroll 1
+        for (int k = 127; k >= 0; --k) {
+            __syncthreads();
+            if (k >= 1) diag4_pivot(rawc, colb + ((k - 1) & 1) * CB, rd, info, base_index, k - 1, lane);
+        }
+        __syncthreads();
+        return;
+    }
+    float r[8][8], t[8][8];                              // 64 independent loads per thread: one memory latency
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int row = a * 16 + ty, col = b * 16 + tx;
+            r[a][b] = (col >= row) ? __ldcg(&Ablk[(int64_t)row * lda + col]) : 0.f;   // L2: written by the kernel just before (PDL)
+            t[a][b] = (a == b && tx == ty) ? 1.f : 0.f;
+        }
+    diag4_handover<7>(r, t, rawc, trow + CB, 15, tx, ty, warp);                  // step 127 (odd -> buffer 1)
+    diag4_block<7>(r, t, colb, trow, rawc, rd, tx, ty, warp);
+    diag4_block<6>(r, t, colb, trow, rawc, rd, tx, ty, warp);
+    diag4_block<5>(r, t, colb, trow, rawc, rd, tx, ty, warp);
+    diag4_block<4>(r, t, colb, trow, rawc, rd, tx, ty, warp);
+    diag4_block<3>(r, t, colb, trow, rawc, rd, tx, ty, warp);
+    diag4_block<2>(r, t, colb, trow, rawc, rd, tx, ty, warp);
+    diag4_block<1>(r, t, colb, trow, rawc, rd, tx, ty, warp);
+    diag4_block<0>(r, t, colb, trow, rawc, rd, tx, ty, warp);
+    __syncthreads();                                     // every rd[] entry visible
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const int row = a * 16 + ty;
+        const float ri = rd[row];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const int col = b * 16 + tx;
+            Dinv[(int64_t)row * ldd + col] = (col >= row) ? t[a][b] * ri : 0.f;       // V = diag(R)^-1 T
+        }
+    }
+}
+
 // ------------------------------------------------------------------ diagonal block, second generation
 // Same contract as chol_diag_kernel (A_jj upper triangle in, Dinv = R_jj^-1 out with A_jj = R_jj R_jj^T), organised
 // like the outer recursion instead of 256 barrier-separated rank-1 steps:
@@ -451,10 +733,11 @@ chol_diag2_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict
 // Every product is a square-ish fp32 GEMM with triangular-operand k-range skipping.
 static int diag_kernel_from_env() {
     const char* e = getenv("GPTQ_B200_DIAG_KERNEL");
-    return (e && e[0] == '2') ? 2 : 1;
+    if (e && e[0] >= '1' && e[0] <= '4') return e[0] - '0';
+    return 4;
 }
-// 1 = register-tile kernel (default, 58 us), 2 = recursive shared-memory kernel (GPTQ_B200_DIAG_KERNEL=2; measured 64 us:
-// its single-warp 32x32 base case exposes every shuffle / shared-memory latency)
+// 4 = fused factor + inverse with a dedicated pivot warp (default), 3 = fused without it, 1 = two-phase register-tile kernel (58 us), 2 = recursive
+// shared-memory kernel (measured 64 us: its single-warp 32x32 base case exposes every shuffle / shared-memory latency)
 static int g_diag_kernel = diag_kernel_from_env();
 
 struct HinvCtx {
@@ -467,7 +750,13 @@ static void hinv_rec(HinvCtx& c, int a, int b) {
         const int c0 = a * CB;
         const bool pdl_ok = !c.first;      // the very first kernel follows the memsets of info / U
         c.first = false;
-        cudaError_t e = g_diag_kernel == 2
+        cudaError_t e = g_diag_kernel == 4
+            ? launch_pdl(pdl_ok, chol_diag4_kernel, dim3(1), dim3(288), (size_t)0, c.st, c.A + (int64_t)c0 * c.lda + c0, c.lda,
+                         c.V + (int64_t)c0 * c.ldv + c0, c.ldv, c.info, c0)
+            : g_diag_kernel == 3
+            ? launch_pdl(pdl_ok, chol_diag3_kernel, dim3(1), dim3(256), (size_t)0, c.st, c.A + (int64_t)c0 * c.lda + c0, c.lda,
+                         c.V + (int64_t)c0 * c.ldv + c0, c.ldv, c.info, c0)
+            : g_diag_kernel == 2
             ? launch_pdl(pdl_ok, chol_diag2_kernel, dim3(1), dim3(256), (size_t)DIAG2_SMEM, c.st, c.A + (int64_t)c0 * c.lda + c0, c.lda,
                          c.V + (int64_t)c0 * c.ldv + c0, c.ldv, c.info, c0)
             : launch_pdl(pdl_ok, chol_diag_kernel, dim3(1), dim3(256), c.smem, c.st, c.A + (int64_t)c0 * c.lda + c0, c.lda,
