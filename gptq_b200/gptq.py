@@ -12,8 +12,11 @@ What differs underneath:
   tcgen05 syrk (lower tiles only).  ``H`` = (2/nsamples) * S, mirrored, is materialised when
   read -- the closed form of the running update at gptq.py:59-65.
 * ``fasterquant`` runs the prologue, the inverse-Cholesky chain, the column loop and the
-  un-permute/cast epilogue as C-ABI calls on the current CUDA stream; the only host syncs are the
-  ones the reference also has (``quantizer.ready()``, the final ``synchronize`` + ``.item()``).
+  un-permute/cast epilogue as C-ABI calls on the current CUDA stream; the only host sync is the
+  one the reference also has (gptq.py:292), reduced to ONE small record read back per call.
+* Linears whose hooks receive the very same tensor (q/k/v, gate/up) share one accumulator, one
+  prologue and one chain (``_Accumulator``), verified bit-exact on the device; small row shards of
+  such linears are solved in one stacked column loop (``_solve_rows``).
 
 Extras the reference does not expose (needed for packing grouped models, tests and sharding):
 ``codes`` (uint8 [R,K]), ``scales`` / ``zeros`` ([R,ngroups]), ``g_idx`` ([K]), ``perm``, ``error``.
