@@ -28,16 +28,13 @@ namespace gq {
 extern int g_gemm_splitk;
 extern int g_gemm_splitk_minkb;
 extern int g_gemm_trunc;
+extern int g_gemm_bk;
 extern int g_small_gemm_max;
 
-constexpr int GT_BM = 128, GT_BN = 256, GT_BK = 32;
-constexpr int GT_STAGES = 2;
-constexpr int GT_A_BYTES = GT_BM * GT_BK * 4;        // 16 KB
-constexpr int GT_B_BYTES = GT_BN * GT_BK * 4;        // 32 KB
-constexpr int GT_STAGE_BYTES = 2 * (GT_A_BYTES + GT_B_BYTES);   // hi + lo of both operands = 96 KB
+constexpr int GT_BM = 128, GT_BN = 256;
+constexpr int GT_RING_BYTES = 192 * 1024;             // operand ring: 2 stages of BK = 32 or 4 stages of BK = 16
 constexpr int GT_THREADS = 320;
-constexpr int GT_CHUNK = 1;                           // k-blocks per TMEM accumulation chain (12 MMAs)
-constexpr int GT_SMEM = GT_STAGES * GT_STAGE_BYTES + 1024 + 256;
+constexpr int GT_SMEM = GT_RING_BYTES + 1024 + 256;
 
 constexpr int GT_TP = GT_BM + 4;                      // pitch of the transposed partial tile in shared memory (split-K):
                                                       // 16-byte aligned columns, conflict-free for float4 reads along the columns
@@ -55,8 +52,22 @@ __device__ __forceinline__ float rn_tf32(float x) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// GT_BK = k-extent of one pipeline stage.  32: 2 stages of 96 KB (raw + lo of both operands), K-major tiles are one
+// 128-byte swizzle row; 16: 4 stages of 48 KB, K-major tiles are 64-byte rows (SWIZZLE_64B) -- same bytes in flight, but
+// a TMA round trip overlaps three other stages instead of one.  The accumulation chain is 12 MMAs either way.
+// Measured on B200 at 4096^3: BK = 32 -> 160 TFLOP/s, BK = 16 -> 140 TFLOP/s (twice the barrier hand-offs, no gain from the
+// deeper ring: the kernel is limited by shared-memory traffic, not by exposed TMA latency), so 32 is the default
+// (GPTQ_B200_GEMM_BK=16 selects the other instantiation; both pass the parity tests).
+template <int GT_BK>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+    constexpr int GT_A_BYTES = GT_BM * GT_BK * 4;
+    constexpr int GT_B_BYTES = GT_BN * GT_BK * 4;
+    constexpr int GT_STAGE_BYTES = 2 * (GT_A_BYTES + GT_B_BYTES);
+    constexpr int GT_STAGES = GT_RING_BYTES / GT_STAGE_BYTES;
+    constexpr int GT_CHUNK = 32 / GT_BK;              // k-blocks per TMEM accumulation chain: 12 MMAs (24 measured +2 % speed,
+                                                      // twice the truncation bias; the drain is not the limiter)
+    constexpr int GT_PANEL = 32 * GT_BK * 4;          // one MN-major TMA box: 32 m/n x GT_BK k
     const int m0 = blockIdx.y * GT_BM, n0 = blockIdx.x * GT_BN;
     if ((p.mode & SG_UPPER_TILES) && n0 + GT_BN - 1 < m0) return;      // whole CTA, before any barrier
     int kbeg = 0, kend = p.Kd;
@@ -112,13 +123,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], GT_A_BYTES + GT_B_BYTES);
                 if (p.a_mn) {
 #pragma unroll
-                    for (int q = 0; q < GT_BM / 32; ++q) ptx::tma_load_2d(sA + q * 4096, &tmA, &full_bar[stage], m0 + q * 32, k0);
+                    for (int q = 0; q < GT_BM / 32; ++q) ptx::tma_load_2d(sA + q * GT_PANEL, &tmA, &full_bar[stage], m0 + q * 32, k0);
                 } else {
                     ptx::tma_load_2d(sA, &tmA, &full_bar[stage], k0, m0);
                 }
                 if (p.b_mn) {
 #pragma unroll
-                    for (int q = 0; q < GT_BN / 32; ++q) ptx::tma_load_2d(sB + q * 4096, &tmB, &full_bar[stage], n0 + q * 32, k0);
+                    for (int q = 0; q < GT_BN / 32; ++q) ptx::tma_load_2d(sB + q * GT_PANEL, &tmB, &full_bar[stage], n0 + q * 32, k0);
                 } else {
                     ptx::tma_load_2d(sB, &tmB, &full_bar[stage], k0, n0);
                     ptx::tma_load_2d(sB + GT_B_BYTES / 2, &tmB, &full_bar[stage], k0, n0 + 128);
@@ -143,14 +154,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t d_tmem = tmem_base + buf * GT_BN;
 #pragma unroll
                 for (int ks = 0; ks < GT_BK / 8; ++ks) {
-                    // K-major: +32 B per k-step inside the 128 B swizzle row; MN-major: +1024 B (8 k-rows)
+                    // K-major: +32 B per k-step inside the swizzle row; MN-major: +1024 B (8 k-rows)
                     const uint32_t aoff = p.a_mn ? ks * 1024 : ks * 32;
                     const uint32_t boff = p.b_mn ? ks * 1024 : ks * 32;
-                    // K-major: SWIZZLE_128B, 8-row atoms (SBO 1024).  MN-major tf32: SWIZZLE_128B_BASE32B, 32-element x
-                    // 4-k-row atoms: LBO = panel stride (next 32 m/n), SBO = 512 (next 4 k-rows).
-                    const uint32_t albo = p.a_mn ? 4096 : 16, blbo = p.b_mn ? 4096 : 16;
-                    const uint32_t asbo = p.a_mn ? 512 : 1024, bsbo = p.b_mn ? 512 : 1024;
-                    const uint32_t alt = p.a_mn ? 1 : 2, blt = p.b_mn ? 1 : 2;
+                    // K-major: SWIZZLE_128B (BK = 32) or SWIZZLE_64B (BK = 16), 8-row atoms (SBO = 8 rows).  MN-major tf32:
+                    // SWIZZLE_128B_BASE32B, 32-element x 4-k-row atoms: LBO = panel stride (next 32 m/n), SBO = 512.
+                    constexpr uint32_t KSBO = 8 * GT_BK * 4, KLT = (GT_BK == 32) ? 2 : 4;
+                    const uint32_t albo = p.a_mn ? GT_PANEL : 16, blbo = p.b_mn ? GT_PANEL : 16;
+                    const uint32_t asbo = p.a_mn ? 512 : KSBO, bsbo = p.b_mn ? 512 : KSBO;
+                    const uint32_t alt = p.a_mn ? 1 : KLT, blt = p.b_mn ? 1 : KLT;
                     const uint64_t ahi = ptx::make_smem_desc(sA + aoff, albo, asbo, alt);
                     const uint64_t alo = ptx::make_smem_desc(sA + GT_A_BYTES + aoff, albo, asbo, alt);
                     const uint64_t bhi = ptx::make_smem_desc(sB + boff, blbo, bsbo, blt);
@@ -342,17 +354,17 @@ static EncodeTiledFn2 get_encode_fn2() {
 }
 
 // Operand with logical shape [mn_extent x k_extent].  mn_major: stored [k][mn] (mn contiguous), else [mn][k].
-static int make_operand_map(CUtensorMap* tm, const float* ptr, int64_t ld, int mn_extent, int k_extent, bool mn_major) {
+static int make_operand_map(CUtensorMap* tm, const float* ptr, int64_t ld, int mn_extent, int k_extent, bool mn_major, int bk) {
     EncodeTiledFn2 enc = get_encode_fn2();
     if (!enc) return set_err(999, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2], gstr[1];
     cuuint32_t box[2], estr[2] = {1, 1};
-    if (mn_major) { gdim[0] = (cuuint64_t)mn_extent; gdim[1] = (cuuint64_t)k_extent; box[0] = 32; box[1] = GT_BK; }
-    else          { gdim[0] = (cuuint64_t)k_extent; gdim[1] = (cuuint64_t)mn_extent; box[0] = GT_BK; box[1] = 128; }
+    if (mn_major) { gdim[0] = (cuuint64_t)mn_extent; gdim[1] = (cuuint64_t)k_extent; box[0] = 32; box[1] = (cuuint32_t)bk; }
+    else          { gdim[0] = (cuuint64_t)k_extent; gdim[1] = (cuuint64_t)mn_extent; box[0] = (cuuint32_t)bk; box[1] = 128; }
     gstr[0] = (cuuint64_t)ld * 4;
     CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return set_err(1000 + (int)cr, "cuTensorMapEncodeTiled(fp32) failed (%d)", (int)cr);
@@ -368,13 +380,15 @@ int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, co
                    int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st) {
     if (M <= 0 || N <= 0) return 0;
     CUtensorMap tmA, tmB;
-    int rc = make_operand_map(&tmA, A, lda, M, Kd, transa != 0);
+    const int bk = g_gemm_bk == 16 ? 16 : 32;
+    int rc = make_operand_map(&tmA, A, lda, M, Kd, transa != 0, bk);
     if (rc) return rc;
-    rc = make_operand_map(&tmB, B, ldb, N, Kd, transb == 0);
+    rc = make_operand_map(&tmB, B, ldb, N, Kd, transb == 0, bk);
     if (rc) return rc;
     static bool attr_done = false;
     if (!attr_done) {
-        GQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+        GQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
+        GQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
         attr_done = true;
     }
     GemmTcParams p;
@@ -390,7 +404,7 @@ int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, co
         for (int y = 0; y < gy; ++y)
             for (int x = 0; x < gx; ++x) tiles += (x * GT_BN + GT_BN - 1 >= y * GT_BM) ? 1 : 0;
     }
-    const int nkb = cdiv(Kd, GT_BK);
+    const int nkb = cdiv(Kd, 32);
     int S = 1;
     if (g_gemm_splitk)
         while (S * 2 <= 8 && tiles * S * 2 <= num_sms() && nkb / (S * 2) >= g_gemm_splitk_minkb) S *= 2;
@@ -414,7 +428,8 @@ int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, co
         ++na;
     }
     cfg.attrs = at; cfg.numAttrs = na;
-    GQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel, tmA, tmB, p));
+    if (bk == 16) GQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<16>, tmA, tmB, p));
+    else GQ_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<32>, tmA, tmB, p));
     GQ_LAUNCHED();
     return 0;
 }
@@ -435,6 +450,7 @@ static int int_from_env(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 int g_small_gemm_max = int_from_env("GPTQ_B200_SMALL_GEMM_MAX", 512);   // M, N up to which gemm_fp32 uses sgemm_small.cu
+int g_gemm_bk = int_from_env("GPTQ_B200_GEMM_BK", 32);                // k-extent of a pipeline stage (32: 2 stages, 16: 4 stages)
 int g_gemm_trunc = int_from_env("GPTQ_B200_GEMM_TRUNC", 1);            // see the converter in gemm_tc_kernel
 int g_gemm_splitk_minkb = int_from_env("GPTQ_B200_SPLITK_MINKB", 4);   // fewest k-blocks (of 32) a split may get
 int g_pdl = flag_from_env("GPTQ_B200_PDL", 1);
