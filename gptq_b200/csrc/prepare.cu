@@ -83,30 +83,39 @@ argsort_desc_kernel(const float* __restrict__ v, int n, int32_t* __restrict__ pe
 }
 
 // ------------------------------------------------------------------ W[:, perm]
-__global__ void permute_cols_kernel(const float* __restrict__ W, int R, int K, int64_t ldw, const int32_t* __restrict__ perm,
-                                    float* __restrict__ out, int64_t ldo) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= K) return;
-    int src = perm ? perm[c] : c;
-    for (int r = blockIdx.y; r < R; r += gridDim.y) out[(int64_t)r * ldo + c] = W[(int64_t)r * ldw + src];
+// One CTA per row: the gather W[r, perm[c]] then reads from a row that stays in L1 (a CTA covering only 256 columns
+// would pull the whole row through L2 for 1 KB of output).
+__global__ void __launch_bounds__(256)
+permute_cols_kernel(const float* __restrict__ W, int R, int K, int64_t ldw, const int32_t* __restrict__ perm,
+                    float* __restrict__ out, int64_t ldo) {
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        const float* src = W + (int64_t)r * ldw;
+        float* dst = out + (int64_t)r * ldo;
+        for (int c = threadIdx.x; c < K; c += blockDim.x) dst[c] = src[perm ? perm[c] : c];
+    }
 }
 
 // ------------------------------------------------------------------ H[perm][:,perm] + damp, padded
-__global__ void hessian_gather_kernel(const float* __restrict__ H, int K, int64_t ldh, const int32_t* __restrict__ perm,
-                                      const float* __restrict__ damp, float* __restrict__ A, int Kp, int64_t lda) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
-    int i = blockIdx.y;
-    if (j >= Kp) return;
-    float v;
-    if (i < K && j < K) {
-        int pi = perm ? perm[i] : i;
-        int pj = perm ? perm[j] : j;
-        v = H[(int64_t)pi * ldh + pj];
-        if (i == j && damp) v = __fadd_rn(v, *damp);
-    } else {
-        v = (i == j) ? 1.f : 0.f;
+__global__ void __launch_bounds__(256)
+hessian_gather_kernel(const float* __restrict__ H, int K, int64_t ldh, const int32_t* __restrict__ perm,
+                      const float* __restrict__ damp, float* __restrict__ A, int Kp, int64_t lda) {
+    // one CTA per output row: row perm[i] of H stays in L1 while it is gathered by perm[j]
+    for (int i = blockIdx.x; i < Kp; i += gridDim.x) {
+        float* dst = A + (int64_t)i * lda;
+        if (i < K) {
+            const float* src = H + (int64_t)(perm ? perm[i] : i) * ldh;
+            for (int j = threadIdx.x; j < Kp; j += blockDim.x) {
+                float v = 0.f;
+                if (j < K) {
+                    v = src[perm ? perm[j] : j];
+                    if (i == j && damp) v = __fadd_rn(v, *damp);
+                }
+                dst[j] = v;
+            }
+        } else {
+            for (int j = threadIdx.x; j < Kp; j += blockDim.x) dst[j] = (i == j) ? 1.f : 0.f;
+        }
     }
-    A[(int64_t)i * lda + j] = v;
 }
 
 // ------------------------------------------------------------------ mirror lower -> upper
@@ -206,15 +215,19 @@ __global__ void compare_rows_kernel(const uint16_t* __restrict__ a, int64_t lda,
 
 // ------------------------------------------------------------------ Q[:, invperm] + cast
 template <typename T>
-__global__ void finalize_kernel(const float* __restrict__ Q, int64_t ldq, const uint8_t* __restrict__ codes, int64_t ldc, int R,
-                                int K, const int32_t* __restrict__ invperm, T* __restrict__ wout, int64_t ldwo,
-                                uint8_t* __restrict__ cout, int64_t ldco) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= K) return;
-    int src = invperm ? invperm[c] : c;
-    for (int r = blockIdx.y; r < R; r += gridDim.y) {
-        if (wout) wout[(int64_t)r * ldwo + c] = from_f32<T>(Q[(int64_t)r * ldq + src]);
-        if (cout) cout[(int64_t)r * ldco + c] = codes[(int64_t)r * ldc + src];
+__global__ void __launch_bounds__(256)
+finalize_kernel(const float* __restrict__ Q, int64_t ldq, const uint8_t* __restrict__ codes, int64_t ldc, int R,
+                int K, const int32_t* __restrict__ invperm, T* __restrict__ wout, int64_t ldwo,
+                uint8_t* __restrict__ cout, int64_t ldco) {
+    // one CTA per row (see permute_cols_kernel)
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        const float* q = Q + (int64_t)r * ldq;
+        const uint8_t* cd = codes ? codes + (int64_t)r * ldc : nullptr;
+        for (int c = threadIdx.x; c < K; c += blockDim.x) {
+            const int src = invperm ? invperm[c] : c;
+            if (wout) wout[(int64_t)r * ldwo + c] = from_f32<T>(q[src]);
+            if (cout) cout[(int64_t)r * ldco + c] = cd[src];
+        }
     }
 }
 
@@ -288,7 +301,7 @@ extern "C" int gptq_b200_permute_cols(const float* W, int R, int K, int64_t ldw,
     GQ_ARG(W, 1, "null"); GQ_ARG(R >= 0, 2, "R<0"); GQ_ARG(K >= 0, 3, "K<0"); GQ_ARG(ldw >= K, 4, "ldw<K");
     GQ_ARG(out, 6, "null"); GQ_ARG(ldo >= K, 7, "ldo<K");
     if (R == 0 || K == 0) return 0;
-    permute_cols_kernel<<<grid_cols_rows(K, R, 256), 256, 0, as_stream(stream)>>>(W, R, K, ldw, perm, out, ldo);
+    permute_cols_kernel<<<R < 65535 ? R : 65535, 256, 0, as_stream(stream)>>>(W, R, K, ldw, perm, out, ldo);
     GQ_LAUNCHED();
     return 0;
 }
@@ -297,7 +310,7 @@ extern "C" int gptq_b200_hessian_gather(const float* H, int K, int64_t ldh, cons
                                         float* A, int Kp, int64_t lda, void* stream) {
     GQ_ARG(H, 1, "null"); GQ_ARG(K > 0, 2, "K<=0"); GQ_ARG(ldh >= K, 3, "ldh<K"); GQ_ARG(A, 6, "null");
     GQ_ARG(Kp >= K && Kp % 128 == 0, 7, "Kp must be >= K and a multiple of 128"); GQ_ARG(lda >= Kp, 8, "lda<Kp");
-    hessian_gather_kernel<<<dim3(cdiv(Kp, 256), Kp), 256, 0, as_stream(stream)>>>(H, K, ldh, perm, damp, A, Kp, lda);
+    hessian_gather_kernel<<<Kp < 65535 ? Kp : 65535, 256, 0, as_stream(stream)>>>(H, K, ldh, perm, damp, A, Kp, lda);
     GQ_LAUNCHED();
     return 0;
 }
@@ -373,7 +386,7 @@ extern "C" int gptq_b200_finalize(const float* Q, int64_t ldq, const uint8_t* co
     GQ_ARG(dtype >= 0 && dtype <= 2, 9, "dtype");
     GQ_ARG(!codes_out || codes, 3, "codes_out needs codes");
     if (R == 0 || K == 0) return 0;
-    dim3 g = grid_cols_rows(K, R, 256);
+    const int g = R < 65535 ? R : 65535;
     cudaStream_t st = as_stream(stream);
     if (dtype == GPTQ_B200_F16) finalize_kernel<__half><<<g, 256, 0, st>>>(Q, ldq, codes, ldc, R, K, invperm, (__half*)weight_out, ldwo, codes_out, ldco);
     else if (dtype == GPTQ_B200_BF16) finalize_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(Q, ldq, codes, ldc, R, K, invperm, (__nv_bfloat16*)weight_out, ldwo, codes_out, ldco);
