@@ -48,11 +48,11 @@ __device__ __forceinline__ float div_by_recip(float a, float b, float y) {
     return q;
 }
 
-// LPR = lanes per row: 4 (32 columns per lane) or 8 (16 columns per lane).  With few rows per SM (R <= ~40 x #SMs) the
-// 8-lane form doubles the warps per scheduler, which is what a latency-bound recurrence needs; with many rows the
-// 4-lane form has less redundant quantizer arithmetic per column.
+// LPR = lanes per row: 4 (32 columns per lane) or 8 (16 columns per lane).  The 8-lane form doubles the warps per
+// scheduler, which is what a latency-bound recurrence needs (58 -> 33 us per block at 32 rows per CTA, still 2-3 % ahead
+// at 80 rows); the 4-lane form remains for slabs of 81-96 rows (register file: 8 lanes x 96 rows would not fit).
 template <int LPR>
-__global__ void __launch_bounds__(BQ_MAX_ROWS * 4, 1)
+__global__ void __launch_bounds__(LPR == 8 ? 640 : BQ_MAX_ROWS * 4, 1)
 blockquant_kernel(BQArgs a) {
     constexpr int NW = BQ_B / LPR;           // W1 columns held per lane
     constexpr int NCH = NW / 4;              // chunks of 4 consecutive columns per lane
@@ -248,9 +248,10 @@ blockquant_kernel(BQArgs a) {
 
 static int bq_lpr8_from_env() {
     const char* e = getenv("GPTQ_B200_BQ_LPR8_MAX_ROWS");
-    return e ? atoi(e) : 40;
+    return e ? atoi(e) : 80;
 }
-static int g_bq_lpr8_max_rows = bq_lpr8_from_env();      // rows per CTA up to which the 8-lanes-per-row kernel is used (<= 48)
+static int g_bq_lpr8_max_rows = bq_lpr8_from_env();      // rows per CTA up to which the 8-lanes-per-row kernel is used (<= 80:
+                                                          // 640 threads; measured 2-3 % faster than 4 lanes even at 80 rows)
 
 // Counts (a,b) pairs for which div_by_recip(a, b, RN(1/b)) differs from div.rn.f32(a, b).
 __global__ void selftest_div_kernel(uint64_t n, uint32_t seed, int mode, unsigned long long* mismatches) {
