@@ -60,6 +60,17 @@ def _worker(rank, world, port, rows):
                     @ torch.randn(64, 16, generator=torch.Generator().manual_seed(r))) for r in range(world))
         assert torch.allclose(fake._S, want, atol=1e-5)
         assert fake.nsamples == sum(64 // 2 + r for r in range(world))
+        # linears sharing one accumulator (same activations) are reduced ONCE; the siblings only pick up the global count
+        class _Acc:
+            reduced, count = False, 0
+        acc = _Acc()
+        S = X.t() @ X
+        a, b = _FakeGPTQ(S, 10 + rank), _FakeGPTQ(S, 10 + rank)
+        a._acc = b._acc = acc
+        gd.allreduce_hessian(a)
+        gd.allreduce_hessian(b)
+        assert torch.allclose(S, want, atol=1e-5)                      # summed once, not twice
+        assert a.nsamples == b.nsamples == acc.count == sum(10 + r for r in range(world)) and acc.reduced
         # exchange #2: row shards (uneven on purpose)
         full = torch.arange(rows * 5, dtype=torch.float32).reshape(rows, 5)
         lo, hi = gd.shard_range(rows, rank, world)
