@@ -450,276 +450,6 @@ chol_diag4_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict
     }
 }
 
-// ------------------------------------------------------------------ diagonal block, second generation
-// Same contract as chol_diag_kernel (A_jj upper triangle in, Dinv = R_jj^-1 out with A_jj = R_jj R_jj^T), organised
-// like the outer recursion instead of 256 barrier-separated rank-1 steps:
-//   * the 128x128 block lives in shared memory as 4x4 blocks of 32;
-//   * a 32x32 diagonal block is factored AND inverted by ONE warp with the matrix in registers (lane = row for the
-//     backward Cholesky, lane = column for the triangular inverse), operands exchanged by shuffles: no block barrier
-//     inside the 64 sequential steps, and the next pivot is kept in a dedicated register so that the step-to-step
-//     dependency is shuffle -> rsqrt -> multiply -> fma;
-//   * everything between diagonal blocks is the recursion of hinv_rec on 32- and 64-wide operands, as fp32 FMA
-//     GEMMs from shared memory by all 256 threads (float4 operand loads, triangular k-ranges skipped).
-constexpr int DP = 132;                       // shared-memory pitch (floats): 16-byte aligned rows, 4-bank skew per row
-constexpr int DIAG2_SMEM = ((2 * CB + 64) * DP + 96) * (int)sizeof(float);
-
-// Shared-memory layout of the diagonal-block kernel (floats, from the dynamic shared-memory base):
-//   As [128][DP] A (upper triangle; the lower mirror is Tt scratch) | Vs [128][DP] R^-1 | Ss [64][DP] scratch |
-//   cb [2][32] column exchange | rds [32] reciprocal diagonal
-extern __shared__ __align__(16) float dsm[];
-constexpr int D_AS = 0, D_VS = CB * DP, D_SS = 2 * CB * DP, D_CB = (2 * CB + 64) * DP, D_RD = D_CB + 64;
-
-// 32x32 base case at block offset c0, executed by one warp; lane = matrix row in phase 1, column in phase 2.
-// A single warp issues in order and cannot hide latency by switching, so every step is written as straight
-// batches: all loads, then all FMAs, then all stores, with NO data-dependent branches (columns that must not
-// change see a zero multiplier).  The loops over the 32 steps stay rolled (instruction-cache resident).
-__device__ __noinline__ void diag32_warp(int c0, int32_t* info, int base_index, int lane) {
-    float* Arow = dsm + D_AS + (c0 + lane) * DP + c0;                       // row `lane` of the block
-    float* cb = dsm + D_CB;
-    float* rds = dsm + D_RD;
-    float dg = Arow[lane];                                                  // own diagonal entry A[lane][lane]
-    float anext = Arow[31];                                                 // A[lane][j] for the coming step
-    // ---- backward Cholesky A = R R^T, columns 31 .. 0; afterwards Arow[j] = R[lane][j] (0 for lane > j)
-#pragma unroll 1
-    for (int j = 31; j >= 0; --j) {
-        const float aprev = Arow[j > 0 ? j - 1 : 0];                        // A[lane][j-1] before this step's update
-        const float d = __shfl_sync(0xffffffffu, dg, j);
-        const float rinv = inv_sqrt(d);
-        float c = anext * rinv;
-        if (lane == j) c = d * rinv;                                        // sqrt(d)
-        if (lane > j) c = 0.f;
-        const float cx = lane < j ? c : 0.f;                                // multiplier seen by the other rows
-        anext = fmaf(-c, __shfl_sync(0xffffffffu, cx, j > 0 ? j - 1 : 0), aprev);   // next column first (dependency chain)
-        dg = fmaf(-c, c, dg);
-        float* buf = cb + (j & 1) * 32;
-        buf[lane] = cx;
-        if (lane == j) {
-            rds[j] = rinv;
-            if (!(d > 0.f)) atomicCAS(info, 0, base_index + c0 + j + 1);
-        }
-        __syncwarp();
-        float4 ck[8], av[8];
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-            ck[k4] = *reinterpret_cast<const float4*>(buf + 4 * k4);
-            av[k4] = *reinterpret_cast<const float4*>(Arow + 4 * k4);
-        }
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {                                    // A[i][k] -= R[i][j] R[k][j]  (buf[k] = 0 for k >= j)
-            av[k4].x = fmaf(-c, ck[k4].x, av[k4].x); av[k4].y = fmaf(-c, ck[k4].y, av[k4].y);
-            av[k4].z = fmaf(-c, ck[k4].z, av[k4].z); av[k4].w = fmaf(-c, ck[k4].w, av[k4].w);
-        }
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) *reinterpret_cast<float4*>(Arow + 4 * k4) = av[k4];
-        Arow[j] = c;                                                        // column j is final: R[lane][j]
-    }
-    __syncwarp();
-    // ---- V = R^-1 (upper), lane = column: rows 31 .. 0,  V[i][j] = -(sum_{k>i} R[i][k] V[k][j]) / R[i][i]
-    // Rows of V not yet computed are still zero and R is zero below its diagonal, so the sum runs over all k.
-    float* Vcol = dsm + D_VS + c0 * DP + c0 + lane;                         // V[k][lane] at Vcol[k * DP]
-#pragma unroll 1
-    for (int i = 31; i >= 0; --i) {
-        const float ri = rds[i];
-        const float* Ri = dsm + D_AS + (c0 + i) * DP + c0;                  // row i of R (broadcast reads)
-        float4 r[8];
-        float vk[32];
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) r[k4] = *reinterpret_cast<const float4*>(Ri + 4 * k4);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) vk[k] = Vcol[k * DP];
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int k4 = 0; k4 < 8; ++k4) {
-            s0 = fmaf(r[k4].x, vk[4 * k4 + 0], s0); s1 = fmaf(r[k4].y, vk[4 * k4 + 1], s1);
-            s2 = fmaf(r[k4].z, vk[4 * k4 + 2], s2); s3 = fmaf(r[k4].w, vk[4 * k4 + 3], s3);
-        }
-        const float sum = (s0 + s1) + (s2 + s3);
-        Vcol[i * DP] = (lane > i) ? -ri * sum : (lane == i ? ri : 0.f);
-    }
-}
-
-template <int MT> struct VecLd;
-template <> struct VecLd<4> {
-    static __device__ __forceinline__ void ld(const float* p, float (&o)[4]) {
-        const float4 v = *reinterpret_cast<const float4*>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    }
-};
-template <> struct VecLd<2> {
-    static __device__ __forceinline__ void ld(const float* p, float (&o)[2]) {
-        const float2 v = *reinterpret_cast<const float2*>(p); o[0] = v.x; o[1] = v.y;
-    }
-};
-
-// Out[p][q] = sum_k X[p][k] * Y[q][k]  (p, q, k < N);  X upper triangular (zero for k < p).  All pitches DP.
-// rows / columns interleaved over the 16x16 thread grid (p = tp + 16 i, q = tq + 16 j): float4 loads along k.
-template <int N>
-__device__ __noinline__ void blk_gemm_nt(int xo, int yo, int oo, int tid) {
-    const float* X = dsm + xo; const float* Y = dsm + yo; float* Out = dsm + oo;
-    constexpr int MT = N / 16;
-    const int tp = tid >> 4, tq = tid & 15;
-    float acc[MT][MT];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < MT; ++j) acc[i][j] = 0.f;
-    for (int k = tp & ~3; k < N; k += 4) {
-        float4 x[MT], y[MT];
-#pragma unroll
-        for (int i = 0; i < MT; ++i) x[i] = *reinterpret_cast<const float4*>(X + (tp + 16 * i) * DP + k);
-#pragma unroll
-        for (int j = 0; j < MT; ++j) y[j] = *reinterpret_cast<const float4*>(Y + (tq + 16 * j) * DP + k);
-#pragma unroll
-        for (int i = 0; i < MT; ++i)
-#pragma unroll
-            for (int j = 0; j < MT; ++j) {
-                float t = acc[i][j];
-                t = fmaf(x[i].x, y[j].x, t); t = fmaf(x[i].y, y[j].y, t);
-                t = fmaf(x[i].z, y[j].z, t); t = fmaf(x[i].w, y[j].w, t);
-                acc[i][j] = t;
-            }
-    }
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < MT; ++j) Out[(tp + 16 * i) * DP + tq + 16 * j] = acc[i][j];
-}
-
-// C[p][q] -= sum_k T[k][p] * T[k][q]  for the tiles touching p <= q  (p, q, k < N).  Consecutive MT x MT tiles.
-template <int N>
-__device__ __noinline__ void blk_syrk_tn(int to, int co, int tid) {
-    const float* T = dsm + to; float* C = dsm + co;
-    constexpr int MT = N / 16;
-    const int tp = tid >> 4, tq = tid & 15;
-    if (tp > tq) return;
-    float acc[MT][MT];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < MT; ++j) acc[i][j] = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < N; ++k) {
-        float a[MT], b[MT];
-        VecLd<MT>::ld(T + k * DP + MT * tp, a);
-        VecLd<MT>::ld(T + k * DP + MT * tq, b);
-#pragma unroll
-        for (int i = 0; i < MT; ++i)
-#pragma unroll
-            for (int j = 0; j < MT; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < MT; ++j) C[(MT * tp + i) * DP + MT * tq + j] -= acc[i][j];
-}
-
-// Out[p][q] = -sum_k S[p][k] * V[k][q]  (p, q, k < N);  V upper triangular (zero for k > q).
-// rows interleaved (p = tp + 16 i), columns consecutive (q = MT tq + j); tq is the slow thread index so that a
-// warp's k-range ends at (almost) the same place.
-template <int N>
-__device__ __noinline__ void blk_gemm_nn_neg(int so, int vo, int oo, int tid) {
-    const float* S = dsm + so; const float* V = dsm + vo; float* Out = dsm + oo;
-    constexpr int MT = N / 16;
-    const int tq = tid >> 4, tp = tid & 15;
-    float acc[MT][MT];
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < MT; ++j) acc[i][j] = 0.f;
-    const int kend = min(N, (MT * tq + MT + 3) & ~3);
-    for (int k = 0; k < kend; k += 4) {
-        float4 sv[MT];
-#pragma unroll
-        for (int i = 0; i < MT; ++i) sv[i] = *reinterpret_cast<const float4*>(S + (tp + 16 * i) * DP + k);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            float b[MT];
-            VecLd<MT>::ld(V + (k + kk) * DP + MT * tq, b);
-#pragma unroll
-            for (int i = 0; i < MT; ++i) {
-                const float sik = kk == 0 ? sv[i].x : (kk == 1 ? sv[i].y : (kk == 2 ? sv[i].z : sv[i].w));
-#pragma unroll
-                for (int j = 0; j < MT; ++j) acc[i][j] = fmaf(sik, b[j], acc[i][j]);
-            }
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < MT; ++i)
-#pragma unroll
-        for (int j = 0; j < MT; ++j) Out[(tp + 16 * i) * DP + MT * tq + j] = -acc[i][j];
-}
-
-// One node of the recursion on the range [o, o + 2N) given that both halves' diagonal work is done by `lo` / `hi`:
-//   hi();  Tt = V22 A12^T;  A11 -= Tt^T Tt;  lo();  S = V11 Tt^T;  V12 = -S V22        (see hinv_rec)
-#ifdef GQ_DIAG_TIMING
-#define GQ_STAMP(tag) do { if (tid == 0) { long long t__ = clock64(); printf("diag2 %-10s N=%d o=%d +%lld\n", tag, N, o, t__ - g_t0); g_t0 = t__; } } while (0)
-__device__ long long g_t0;
-#else
-#define GQ_STAMP(tag) do { } while (0)
-#endif
-template <int N, typename Hi, typename Lo>
-__device__ __forceinline__ void diag_node(int o, int tid, Hi hi, Lo lo) {
-    const int m = o + N;
-    hi();
-    __syncthreads();
-    GQ_STAMP("hi");
-    blk_gemm_nt<N>(D_VS + m * DP + m, D_AS + o * DP + m, D_AS + m * DP + o, tid);       // Tt[n2 x n1] into A's lower mirror
-    __syncthreads();
-    GQ_STAMP("g1");
-    blk_syrk_tn<N>(D_AS + m * DP + o, D_AS + o * DP + o, tid);                        // A11 -= Tt^T Tt (upper tiles)
-    __syncthreads();
-    GQ_STAMP("g2");
-    lo();
-    __syncthreads();
-    GQ_STAMP("lo");
-    blk_gemm_nt<N>(D_VS + o * DP + o, D_AS + m * DP + o, D_SS, tid);                    // S = V11 Tt^T
-    __syncthreads();
-    GQ_STAMP("g3");
-    blk_gemm_nn_neg<N>(D_SS, D_VS + m * DP + m, D_VS + o * DP + m, tid);                // V12 = -S V22
-    __syncthreads();
-    GQ_STAMP("g4");
-}
-
-__global__ void __launch_bounds__(256, 1)
-chol_diag2_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict__ Dinv, int64_t ldd,
-                  int32_t* __restrict__ info, int base_index) {
-    float* As = dsm + D_AS;
-    float* Vs = dsm + D_VS;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    ptx::pdl_launch_dependents();
-    for (int idx = tid; idx < CB * (CB / 4); idx += 256) {
-        const int r = idx >> 5, c4 = (idx & 31) * 4;
-        *reinterpret_cast<float4*>(Vs + r * DP + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    ptx::pdl_wait();                          // A_jj carries the preceding GEMM's Schur update (read through L2)
-    const bool avec = ((lda & 3) == 0) && ((reinterpret_cast<uintptr_t>(Ablk) & 15) == 0);
-    {
-        float4 v[16];                                    // 16 independent loads per thread: one memory latency
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const int idx = tid + it * 256, r = idx >> 5, c4 = (idx & 31) * 4;
-            if (avec) v[it] = __ldcg(reinterpret_cast<const float4*>(Ablk + (int64_t)r * lda + c4));
-            else { const float* p = Ablk + (int64_t)r * lda + c4; v[it] = make_float4(__ldcg(p), __ldcg(p + 1), __ldcg(p + 2), __ldcg(p + 3)); }
-        }
-#pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const int idx = tid + it * 256, r = idx >> 5, c4 = (idx & 31) * 4;
-            *reinterpret_cast<float4*>(As + r * DP + c4) = v[it];
-        }
-    }
-    __syncthreads();
-    auto base = [&](int c0) { if (warp == 0) diag32_warp(c0, info, base_index, lane); };
-    auto half = [&](int o) { diag_node<32>(o, tid, [&] { base(o + 32); }, [&] { base(o); }); };
-    diag_node<64>(0, tid, [&] { half(64); }, [&] { half(0); });
-    const bool dvec = ((ldd & 3) == 0) && ((reinterpret_cast<uintptr_t>(Dinv) & 15) == 0);
-    for (int idx = tid; idx < CB * (CB / 4); idx += 256) {
-        const int r = idx >> 5, c4 = (idx & 31) * 4;
-        const float4 v = *reinterpret_cast<const float4*>(Vs + r * DP + c4);
-        float* o = Dinv + (int64_t)r * ldd + c4;
-        if (dvec) *reinterpret_cast<float4*>(o) = v;
-        else { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-    }
-}
-
 // ------------------------------------------------------------------ recursive driver
 // f(a,b) on block range [a,b): on entry A[a:b,a:b] (upper triangle) carries every Schur update from
 // blocks >= b; on exit V[a:b,a:b] = R[a:b,a:b]^-1 (upper).  With the split a < m < b
@@ -733,11 +463,12 @@ chol_diag2_kernel(const float* __restrict__ Ablk, int64_t lda, float* __restrict
 // Every product is a square-ish fp32 GEMM with triangular-operand k-range skipping.
 static int diag_kernel_from_env() {
     const char* e = getenv("GPTQ_B200_DIAG_KERNEL");
-    if (e && e[0] >= '1' && e[0] <= '4') return e[0] - '0';
+    if (e && (e[0] == '1' || e[0] == '3' || e[0] == '4')) return e[0] - '0';
     return 4;
 }
-// 4 = fused factor + inverse with a dedicated pivot warp (default), 3 = fused without it, 1 = two-phase register-tile kernel (58 us), 2 = recursive
-// shared-memory kernel (measured 64 us: its single-warp 32x32 base case exposes every shuffle / shared-memory latency)
+// 4 = fused factor + inverse with a dedicated pivot warp (default, 48.5 us), 3 = fused without it (52 us), 1 = two-phase
+// register-tile kernel (58 us).  A recursive shared-memory kernel with a one-warp 32x32 base case was measured at 64 us
+// and removed (profiles/r01_kernels_ncu_full.md).
 static int g_diag_kernel = diag_kernel_from_env();
 
 struct HinvCtx {
@@ -755,9 +486,6 @@ static void hinv_rec(HinvCtx& c, int a, int b) {
                          c.V + (int64_t)c0 * c.ldv + c0, c.ldv, c.info, c0)
             : g_diag_kernel == 3
             ? launch_pdl(pdl_ok, chol_diag3_kernel, dim3(1), dim3(256), (size_t)0, c.st, c.A + (int64_t)c0 * c.lda + c0, c.lda,
-                         c.V + (int64_t)c0 * c.ldv + c0, c.ldv, c.info, c0)
-            : g_diag_kernel == 2
-            ? launch_pdl(pdl_ok, chol_diag2_kernel, dim3(1), dim3(256), (size_t)DIAG2_SMEM, c.st, c.A + (int64_t)c0 * c.lda + c0, c.lda,
                          c.V + (int64_t)c0 * c.ldv + c0, c.ldv, c.info, c0)
             : launch_pdl(pdl_ok, chol_diag_kernel, dim3(1), dim3(256), c.smem, c.st, c.A + (int64_t)c0 * c.lda + c0, c.lda,
                          c.V + (int64_t)c0 * c.ldv + c0, c.ldv, c.info, c0);
@@ -816,7 +544,6 @@ extern "C" int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, float* U, int
     static bool attr_done = false;
     if (!attr_done) {
         GQ_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GQ_CUDA(cudaFuncSetAttribute(chol_diag2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG2_SMEM));
         attr_done = true;
     }
     GQ_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
