@@ -50,3 +50,19 @@ def hinv_upper_recursive(H, block=128, leaf=fused_block):
         V[s1, s2] = -(V[s1, s1] @ Tt.T) @ V[s2, s2]
     f(0, n // block)
     return V
+
+
+def syrk_tile_order(nbm, sw=12, sh=12):
+    """Python restatement of decode_tile() in csrc/syrk_tc.cu: the order in which the Hessian kernel walks the
+    128-row x 256-column tiles (bi, bj) with bi >= 2 bj -- 2-D chunks of sw column blocks x sh row blocks."""
+    nbn = (nbm + 1) >> 1
+    out = []
+    for sc in range(0, nbn, sw):
+        w = min(sw, nbn - sc)
+        for r0 in range(2 * sc, nbm, sh):
+            r1 = min(r0 + sh, nbm)
+            for j in range(sc, sc + w):
+                lo = max(r0, 2 * j)
+                for bi in range(lo, r1):
+                    out.append((bi, j))
+    return out
