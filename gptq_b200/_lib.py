@@ -14,6 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgptq_b200.so")
 
 F16, BF16, F32 = 0, 1, 2
+ABI_VERSION = 3
+SYRK_AUTO, SYRK_CTA1, SYRK_CTA2 = 0, 1, 2
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -23,8 +25,8 @@ SIGNATURES = {
     "gptq_b200_abi_version": (_i, []),
     "gptq_b200_last_error": (C.c_char_p, []),
     "gptq_b200_launch_count": (_i64, []),
-    "gptq_b200_syrk_workspace_bytes": (_sz, [_i, _i64]),
-    "gptq_b200_syrk_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _f, _f, _i, _vp, _sz, _vp]),
+    "gptq_b200_syrk_workspace_bytes": (_sz, [_i, _i64, _i]),
+    "gptq_b200_syrk_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _f, _f, _i, _i, _vp, _sz, _vp]),
     "gptq_b200_syrk_accum_simt": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _f, _f, _vp]),
     "gptq_b200_symmetrize": (_i, [_vp, _i, _i64, _vp]),
     "gptq_b200_stage_input": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _vp]),
@@ -74,8 +76,8 @@ def load() -> C.CDLL:
             fn.restype = res
             fn.argtypes = args
         ver = lib.gptq_b200_abi_version()
-        if ver != 2:
-            raise GptqB200Error(f"ABI version mismatch: library {ver}, binding 2")
+        if ver != ABI_VERSION:
+            raise GptqB200Error(f"ABI version mismatch: library {ver}, binding {ABI_VERSION}")
         _lib = lib
     return _lib
 

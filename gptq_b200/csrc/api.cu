@@ -15,14 +15,22 @@ int set_err(int code, const char* fmt, ...) {
     return code;
 }
 
+int cur_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    return dev;
+}
+
 int num_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    static std::atomic<int> sms[256] = {};
+    const int dev = cur_device();
+    const int slot = (dev >= 0 && dev < 256) ? dev : 0;
+    int v = sms[slot].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        sms[slot].store(v, std::memory_order_relaxed);
     }
-    return sms;
+    return v;
 }
 
 }  // namespace gq

@@ -541,11 +541,7 @@ extern "C" int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, float* U, int
     GQ_ARG(ws_bytes >= gptq_b200_hinv_upper_workspace_bytes(Kp), 8, "workspace too small");
     cudaStream_t st = as_stream(stream);
     const size_t smem = (size_t)CB * CT * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
-        GQ_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_done = true;
-    }
+    GQ_ONCE_PER_DEVICE(GQ_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     GQ_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     GQ_CUDA(cudaMemset2DAsync(U, ldu * sizeof(float), 0, (size_t)Kp * sizeof(float), Kp, st));
     HinvCtx c{A, lda, U, ldu, static_cast<float*>(ws), info, st, smem, 0, true};

@@ -290,7 +290,7 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
                                  uint8_t* codes, int64_t ldc, float* row_loss, void* ws, size_t ws_bytes, void* stream) {
     GQ_ARG(W, 1, "null"); GQ_ARG(R >= 0, 2, "R<0"); GQ_ARG(K > 0, 3, "K<=0"); GQ_ARG(ldw >= K, 4, "ldw<K");
     GQ_ARG(U, 5, "null"); GQ_ARG(ldu >= K, 6, "ldu<K");
-    GQ_ARG(blocksize > 0 && blocksize <= BQ_B, 7, "blocksize must be in [1,128]");
+    GQ_ARG(blocksize > 0 && (blocksize <= BQ_B || blocksize % BQ_B == 0), 7, "blocksize must be in [1,128] or a multiple of 128");
     GQ_ARG(mode == 0 || mode == 1, 9, "mode must be 0 or 1");
     GQ_ARG(mode == 0 || groupsize > 0, 8, "dynamic groups need groupsize > 0");
     GQ_ARG(scale && zero, 11, "null"); GQ_ARG(ngroups >= 1, 13, "ngroups<1");
@@ -307,30 +307,41 @@ extern "C" int gptq_b200_colloop(float* W, int R, int K, int64_t ldw, const floa
     if (rpc < 8) rpc = 8;
     if (rpc > BQ_MAX_ROWS) rpc = BQ_MAX_ROWS;
     const size_t smem = (size_t)(BQ_B * BQ_B + 3 * rpc * BQ_SP) * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    GQ_ONCE_PER_DEVICE({
         const size_t smem_max = (size_t)(BQ_B * BQ_B + 3 * BQ_MAX_ROWS * BQ_SP) * sizeof(float);
         GQ_CUDA(cudaFuncSetAttribute(blockquant_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
         GQ_CUDA(cudaFuncSetAttribute(blockquant_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-        attr_done = true;
-    }
+    });
     const int lpr = (rpc <= g_bq_lpr8_max_rows) ? 8 : 4;
     GQ_CUDA(cudaMemsetAsync(row_loss, 0, (size_t)R * sizeof(float), st));
     // Two-level lazy update (same arithmetic as gptq.py:276, regrouped): after every block only the rest of the current
     // super-block is brought up to date (narrow GEMM, depth `count`); the columns beyond it receive ONE deep GEMM per
-    // super-block.  Dynamic groups wider than a block read W far ahead (gptq.py:255), so they keep the one-level form.
-    const int sb_blocks = (mode == 1 && groupsize > blocksize) ? 1 : BQ_SUPER;
+    // super-block.  Dynamic groups are fitted by find_params on the GLOBAL W at the start of the block in which they
+    // begin (gptq.py:253-255), and the reference has by then applied every earlier block's update to ALL later columns
+    // (gptq.py:276).  Groups start at multiples of `groupsize`, so a group stays inside one super-block -- where the
+    // near updates keep W current -- iff the super-block width is a multiple of the group size; otherwise (gs = 96,
+    // 100, 1024, blocksize 100 with gs 64, ...) a group would straddle the super-block end and read columns still
+    // waiting for the far GEMM, so those cases keep the one-level form.
+    // A reference block wider than 128 columns (gptq.py:191 accepts any blocksize) is walked in 128-column kernel blocks:
+    // in-block and lazy updates are the same arithmetic, W[:, j] -= err_i * U[i, j], so only the fp32 summation order
+    // differs -- except that dynamic groups are fitted on W as of the start of the REFERENCE block (gptq.py:253-255), which
+    // is why find_params below is keyed on `blocksize`, not on the kernel block.
+    const int kb = blocksize < BQ_B ? blocksize : BQ_B;
+    const int64_t sbw = (int64_t)BQ_SUPER * kb;
+    const bool two_level = (mode == 0) || (sbw % groupsize == 0 && sbw % blocksize == 0);
+    const int sb_blocks = two_level ? BQ_SUPER : 1;
     const int64_t lde = (int64_t)BQ_SUPER * BQ_B;
     int sb_start = 0;
-    for (int i1 = 0, bi = 0; i1 < K; i1 += blocksize, ++bi) {
-        const int i2 = (i1 + blocksize < K) ? i1 + blocksize : K;
+    for (int i1 = 0, bi = 0; i1 < K; i1 += kb, ++bi) {
+        const int i2 = (i1 + kb < K) ? i1 + kb : K;
         const int count = i2 - i1;
         if (bi % sb_blocks == 0) sb_start = i1;
-        int sb_end = sb_start + sb_blocks * blocksize; if (sb_end > K) sb_end = K;
-        if (mode == 1) {
+        int sb_end = sb_start + sb_blocks * kb; if (sb_end > K) sb_end = K;
+        if (mode == 1 && i1 % blocksize == 0) {
+            const int r2 = (i1 + blocksize < K) ? i1 + blocksize : K;          // end of the reference block
             const int first = ((i1 + groupsize - 1) / groupsize) * groupsize;
-            if (first < i2) {
-                const int last = ((i2 - 1) / groupsize) * groupsize;
+            if (first < r2) {
+                const int last = ((r2 - 1) / groupsize) * groupsize;
                 int end = last + groupsize; if (end > K) end = K;
                 int rc = gptq_b200_find_params(W, R, K, ldw, first, end - first, groupsize, maxq, sym, mse, norm, grid,
                                                maxshrink, scale, zero, ngroups, first / groupsize, stream);

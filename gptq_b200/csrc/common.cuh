@@ -24,7 +24,18 @@ int set_err(int code, const char* fmt, ...);
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
-int num_sms();
+int num_sms();       // of the CURRENT device (cached per device)
+int cur_device();
+
+// Function attributes (cudaFuncSetAttribute) and SM counts are per-DEVICE properties: one process may drive several GPUs
+// (a layer on cuda:1 while cuda:0 is current elsewhere), so "done once" is tracked per device ordinal.
+struct PerDeviceOnce {
+    std::atomic<uint64_t> mask[4] = {};
+    bool done(int dev) const { return dev >= 0 && dev < 256 && ((mask[dev >> 6].load(std::memory_order_acquire) >> (dev & 63)) & 1ull); }
+    void mark(int dev) { if (dev >= 0 && dev < 256) mask[dev >> 6].fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+#define GQ_ONCE_PER_DEVICE(...) do { static gq::PerDeviceOnce once__; const int dev__ = gq::cur_device(); \
+    if (!once__.done(dev__)) { __VA_ARGS__; once__.mark(dev__); } } while (0)
 
 // Programmatic dependent launch (GPTQ_B200_PDL, default on): the kernel may be scheduled while its predecessor in the
 // stream is still running; it must execute ptx::pdl_wait() before touching memory the predecessor writes.

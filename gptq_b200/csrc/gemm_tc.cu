@@ -385,12 +385,10 @@ int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, co
     if (rc) return rc;
     rc = make_operand_map(&tmB, B, ldb, N, Kd, transb == 0, bk);
     if (rc) return rc;
-    static bool attr_done = false;
-    if (!attr_done) {
+    GQ_ONCE_PER_DEVICE({
         GQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
         GQ_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM));
-        attr_done = true;
-    }
+    });
     GemmTcParams p;
     p.M = M; p.N = N; p.Kd = Kd; p.alpha = alpha; p.beta = beta; p.C = C; p.ldc = ldc; p.mode = mode;
     p.a_mn = transa ? 1 : 0; p.b_mn = transb ? 0 : 1;

@@ -51,6 +51,7 @@ torch.backends.cudnn.allow_tf32 = False
 
 STAGE_SAMPLES = int(os.environ.get("GPTQ_B200_STAGE_SAMPLES", "16"))
 CHUNK_TOKENS = int(os.environ.get("GPTQ_B200_CHUNK_TOKENS", "0"))     # 0 = library default
+SYRK_VARIANT = int(os.environ.get("GPTQ_B200_SYRK_VARIANT", "0"))     # 0 = auto (CTA-pair kernel), 1 = cta_group::1, 2 = cta_group::2
 EMPTY_CACHE_ON_FREE = os.environ.get("GPTQ_B200_EMPTY_CACHE", "0") == "1"
 # Linears that receive the very same activation tensor (q/k/v, gate/up: their forward hooks see one tensor) share ONE
 # Hessian accumulator, ONE prologue and ONE inverse-Cholesky chain; the reference recomputes all three per linear
@@ -58,7 +59,14 @@ EMPTY_CACHE_ON_FREE = os.environ.get("GPTQ_B200_EMPTY_CACHE", "0") == "1"
 # first holder keeping the tensor alive) AND, with SHARE_VERIFY, bit-identical to the staged copy (device-side compare,
 # checked at fasterquant's own host sync: a mismatch raises instead of producing a different result).
 SHARE_H = os.environ.get("GPTQ_B200_SHARE_H", "1") == "1"
-SHARE_VERIFY = os.environ.get("GPTQ_B200_SHARE_VERIFY", "1") == "1"
+# SHARE_VERIFY: "full" = every shared batch is compared in full; "1" (default) = the first VERIFY_FULL_BATCHES shared
+# batches of an accumulator are compared in full -- which proves that the module really hands ONE unmodified tensor to
+# these linears (a module that changed its input between two sibling hooks would do so in every forward) -- and later
+# batches are compared on every VERIFY_ROW_STRIDE-th row (the pointer / shape / stride / dtype identity and the
+# keep-alive reference are checked for every batch regardless); "0" = identity checks only.
+SHARE_VERIFY = os.environ.get("GPTQ_B200_SHARE_VERIFY", "1")
+VERIFY_FULL_BATCHES = 2
+VERIFY_ROW_STRIDE = 16
 # Linears that share a Hessian and are quantized with the same arguments are solved in ONE column loop (their rows
 # stacked): the loop is latency-bound, so three 4096-row linears cost little more than one.
 GROUP_SIBLINGS = os.environ.get("GPTQ_B200_GROUP_SIBLINGS", "1") == "1"
@@ -123,6 +131,22 @@ def syrk_issued_flops(K: int, tokens: int) -> float:
     return 2.0 * tiles * 128 * 256 * tokens
 
 
+def _on_device(fn):
+    """Run a GPTQ method with the layer's GPU current.  The reference works on any device because torch dispatches per
+    tensor; here every C-ABI launch goes to torch.cuda.current_stream() of the CURRENT device, so a layer living on
+    another GPU of the same process needs the guard (workspaces, streams and per-device kernel attributes follow)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        idx = self.dev.index
+        if idx is None or idx == torch.cuda.current_device():
+            return fn(self, *a, **k)
+        with torch.cuda.device(idx):
+            return fn(self, *a, **k)
+    return wrapped
+
+
 _ACT_DTYPES = (torch.float16, torch.bfloat16, torch.float32)
 _JOINABLE = {}            # (device, batch identity) -> weakref(_Accumulator that has absorbed exactly that one batch)
 
@@ -158,6 +182,8 @@ class _Accumulator:
         self.last = None               # (view of the last batch, count at that time) for GPTQ.input
         self.last_slab = None
         self.flag = None               # device int32, set by compare_rows when a shared batch was NOT identical
+        self.verified = 0              # shared batches compared so far (see SHARE_VERIFY)
+        self.input_mean = None         # (sum over tokens of the last batch, tokens, count): GPTQ.input after fasterquant
         self.reduced = False           # dist.allreduce_hessian already summed S over the ranks
         self.sealed = False
         self.n_final = None
@@ -237,7 +263,7 @@ class _Accumulator:
     def verify(self, x):
         """Device-side proof that `x` is bit-identical to the batch staged last (result read at fasterquant's sync).
         Runs once per sample and sibling: no tensor slicing, plain pointer arithmetic."""
-        if not SHARE_VERIFY:
+        if SHARE_VERIFY == "0":
             return
         if self.flag is None:
             self.flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
@@ -246,7 +272,11 @@ class _Accumulator:
         st = self.stage
         ld = st.stride(0)
         ref_ptr = st.data_ptr() + (self.staged - self.last_tokens) * ld * st.element_size()
-        rc = _lib.load().gptq_b200_compare_rows(x.data_ptr(), x.stride(0), ref_ptr, ld, x.shape[0], self.K,
+        rows, ldx = x.shape[0], x.stride(0)
+        self.verified += 1
+        if SHARE_VERIFY != "full" and self.verified > VERIFY_FULL_BATCHES * max(self.members - 1, 1) and rows >= VERIFY_ROW_STRIDE:
+            rows, ldx, ld = rows // VERIFY_ROW_STRIDE, ldx * VERIFY_ROW_STRIDE, ld * VERIFY_ROW_STRIDE
+        rc = _lib.load().gptq_b200_compare_rows(x.data_ptr(), ldx, ref_ptr, ld, rows, self.K,
                                                 self.flag.data_ptr(), torch.cuda.current_stream().cuda_stream)
         if rc:
             _lib.check(rc, "compare_rows")
@@ -264,7 +294,7 @@ class _Accumulator:
             return
         lib = _lib.load()
         K = self.K
-        need = lib.gptq_b200_syrk_workspace_bytes(K, self.staged)
+        need = lib.gptq_b200_syrk_workspace_bytes(K, self.staged, SYRK_VARIANT)
         if need and (self.ws is None or self.ws.numel() < need):
             self.wait_syrk()                               # the old workspace may still be in use
             self.ws = torch.empty(need, dtype=torch.uint8, device=self.dev)
@@ -273,7 +303,8 @@ class _Accumulator:
             with _prof("syrk", syrk_issued_flops(K, self.staged), (K, self.staged)):
                 _lib.check(lib.gptq_b200_syrk_accum(self.stage.data_ptr(), _lib.dt(self.stage), self.staged, K,
                                                     self.stage.stride(0), self.S.data_ptr(), K, 1.0, 1.0, CHUNK_TOKENS,
-                                                    _lib.ptr(self.ws) if need else 0, need, _lib.stream()), "syrk_accum")
+                                                    SYRK_VARIANT, _lib.ptr(self.ws) if need else 0, need, _lib.stream()),
+                           "syrk_accum")
         if not OVERLAP_SYRK:
             launch()
             self.staged = 0
@@ -347,8 +378,22 @@ class _Accumulator:
         self.dead = torch.empty(K, device=self.dev, dtype=torch.uint8)
         _lib.check(lib.gptq_b200_dead_columns(H.data_ptr(), K, K, self.dead.data_ptr(), _lib.stream()), "dead_columns")
         self.H, self.S, self.n_final, self.sealed = H, None, n, True
+        if self.last is not None:      # gptq.py:63 keeps self.input after fasterquant: reduce it before the slab goes away
+            self.input_mean = _last_input(self)
         self.stage = self.stage_other = self.ws = self.ref = self.last = self.last_slab = None
         return H
+
+
+def _last_input(acc):
+    """gptq.py:62-63: mean over tokens of sqrt(2/n) * (last batch); n = sample count when that batch arrived."""
+    if len(acc.last) == 3:                              # (row offset, tokens, count) in the slab staged last
+        off, tokens, n = acc.last
+        x = acc.last_slab[off:off + tokens, :acc.K]
+    else:
+        x, n = acc.last
+    if x.shape[0] == 0 or n == 0:
+        return torch.zeros(acc.K, device=acc.dev)
+    return math.sqrt(2 / n) * x.float().mean(0)
 
 
 def _solve_hessian(H, K, percdamp, actorder, dead=None):
@@ -525,8 +570,10 @@ class GPTQ:
         self._acc = None               # _Accumulator (allocated with the first batch; may be shared, see SHARE_H)
         self._H = None                 # materialised (2/n)*S, full symmetric, or a user-provided H
         self._consumed = False
+        self._input = None             # gptq.py:63 self.input, kept after the accumulator is released
 
     # ------------------------------------------------------------------ Hessian (gptq.py:38-65)
+    @_on_device
     def add_batch(self, inp, out):
         if DEBUG:
             self.inp1 = inp
@@ -612,6 +659,8 @@ class GPTQ:
     def _release(self):
         acc, self._acc = self._acc, None
         if acc is not None:
+            if acc.input_mean is not None:
+                self._input = acc.input_mean
             acc.members -= 1
             acc.member_refs = [r for r in acc.member_refs if r() is not None and r() is not self]
             acc.spec.pop(id(self), None)
@@ -634,8 +683,12 @@ class GPTQ:
     def H(self):
         """(2/nsamples) * sum x x^T as a full symmetric fp32 matrix (what gptq.py:59-65 maintains)."""
         if self._H is None and not self._consumed:
-            self._H = self._own_accumulator().materialize(self.nsamples)
+            self._H = self._materialize()
         return self._H
+
+    @_on_device
+    def _materialize(self):
+        return self._own_accumulator().materialize(self.nsamples)
 
     @H.setter
     def H(self, value):
@@ -650,17 +703,14 @@ class GPTQ:
     @property
     def input(self):
         """gptq.py:63: mean over tokens of sqrt(2/n) * (last batch)."""
+        if self._input is not None:
+            return self._input
         acc = self._acc
-        if acc is None or acc.last is None:
+        if acc is None or (acc.last is None and acc.input_mean is None):
             raise AttributeError("input")
-        if len(acc.last) == 3:                              # (row offset, tokens, count) in the slab staged last
-            off, tokens, n = acc.last
-            slab = acc.last_slab
-            x = slab[off:off + tokens, :acc.K]
-        else:
-            x, n = acc.last
-        return math.sqrt(2 / n) * x.float().mean(0)
+        return acc.input_mean if acc.last is None else _last_input(acc)
 
+    @_on_device
     def raw_accumulator(self):
         """Unscaled S (after folding in anything still staged) -- what multi-GPU runs all-reduce."""
         acc = self._own_accumulator()
@@ -721,6 +771,7 @@ class GPTQ:
             total += R
         return sibs
 
+    @_on_device
     def fasterquant(self, blocksize=128, percdamp=.01, groupsize=-1, actorder=False, static_groups=False,
                     model_name="opt", layer_name="layer", lut_quant=False, non_linear_quant=False, columnwise=False,
                     row_range=None):
@@ -738,6 +789,11 @@ class GPTQ:
         qcfg = self._qcfg(q)
         if qcfg[0] == 0:
             raise RuntimeError("Quantizer.configure() was not called")
+        if not qcfg[1] and (groupsize != -1 or row_range is not None):
+            # quant.py:53-54,97-103: perchannel=False flattens the slice -> ONE (scale, zero) shared by all rows of a group;
+            # the group kernels and the row sharding here are per-row.  No reference driver uses this combination
+            # (all pass perchannel=True: opt.py:174, llama.py:167, bloom.py:149).
+            raise NotImplementedError("perchannel=False is supported for groupsize=-1 without row sharding only")
         argkey = (int(blocksize), float(percdamp), int(groupsize), bool(actorder), bool(static_groups),
                   None if row_range is None else tuple(row_range), qcfg)
 
@@ -759,7 +815,17 @@ class GPTQ:
                 sol = acc.solves[skey] = _solve_hessian(H, K, percdamp, actorder, dead=acc.dead)
             flag = acc.flag
             ent = acc.spec.pop(id(self), None)          # solved ahead by a sibling?
-            if ent is not None and ent[0] == argkey and not q.ready() and torch.equal(ent[1], W):
+            if ent is not None and ent[0] == argkey and not q.ready() and ent[1].shape == W.shape and ent[1].dtype == W.dtype:
+                # the weights the sibling solved for us must still be the layer's weights: compared on the device into the
+                # accumulator's flag, which is read with the single record below (no extra host sync)
+                if acc.flag is None:
+                    acc.flag = torch.zeros(1, device=dev, dtype=torch.int32)
+                    flag = acc.flag
+                if W.numel():
+                    esz = W.element_size() // 2     # compare_rows works on 16-bit units
+                    _lib.check(_lib.load().gptq_b200_compare_rows(W.data_ptr(), W.stride(0) * esz, ent[1].data_ptr(),
+                                                                  ent[1].stride(0) * esz, R, K * esz, acc.flag.data_ptr(),
+                                                                  _lib.stream()), "compare_rows")
                 out = ent[2]
             sibs = [] if (out is not None or q.ready()) else self._siblings_to_solve_with(acc, argkey, R)
             del H
@@ -783,7 +849,8 @@ class GPTQ:
         self._release()
         if rec[1] != 0:
             raise RuntimeError("GPTQ: a batch assumed identical for linears sharing one Hessian accumulator differed "
-                               "(the tensor was modified between their forward hooks); set GPTQ_B200_SHARE_H=0")
+                               "(the tensor was modified between their forward hooks), or the weights of a linear solved "
+                               "together with a sibling changed before its own fasterquant; set GPTQ_B200_SHARE_H=0")
         bad = int(rec[0])
         if bad != 0:
             raise torch.linalg.LinAlgError(

@@ -153,7 +153,7 @@ def quantize_sequential(model, tokens: torch.Tensor, dev, args: QuantArgs, gptq_
                                        actorder=args.act_order, static_groups=args.static_groups,
                                        layer_name=f"{i}.{name}")
                 quantizers[f"{prefix}.{i}.{name}"] = gptq[name].quantizer
-                extras[f"{prefix}.{i}.{name}"] = {k: getattr(gptq[name], k, None) for k in ("codes", "scales", "zeros", "g_idx", "error")}
+                extras[f"{prefix}.{i}.{name}"] = {k: getattr(gptq[name], k, None) for k in ("codes", "scales", "zeros", "g_idx", "error", "oracle_result")}
                 gptq[name].free()
         for j in range(nsamples):
             outs[j] = _call_layer(layer, inps[j].unsqueeze(0), kwargs)[0]

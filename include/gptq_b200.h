@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GPTQ_B200_ABI_VERSION 2
+#define GPTQ_B200_ABI_VERSION 3
 
 enum { GPTQ_B200_F16 = 0, GPTQ_B200_BF16 = 1, GPTQ_B200_F32 = 2 };
 
@@ -47,10 +47,14 @@ int64_t     gptq_b200_launch_count(void);
  *     untouched -- call gptq_b200_symmetrize() before reading H as a full matrix.
  *     `chunk_tokens` (0 = default) bounds how many tokens are summed inside the tensor-core
  *     accumulator before being added to H in fp32 (round-to-nearest) by the epilogue.
+ *     `variant`: GPTQ_B200_SYRK_AUTO / _CTA2 = the CTA-pair kernel (tcgen05 cta_group::2, M256 x N256 tiles over two SMs
+ *     of a TPC; tiles touching the lower triangle at 256 x 256 granularity), _CTA1 = the single-CTA kernel (M128 x N256).
+ *     Both produce the same H up to fp32 summation order inside the tensor core.
  * ------------------------------------------------------------------------------------------ */
-size_t gptq_b200_syrk_workspace_bytes(int K, int64_t tokens);
+enum { GPTQ_B200_SYRK_AUTO = 0, GPTQ_B200_SYRK_CTA1 = 1, GPTQ_B200_SYRK_CTA2 = 2 };
+size_t gptq_b200_syrk_workspace_bytes(int K, int64_t tokens, int variant);
 int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, int K, int64_t ldx,
-                         float* H, int64_t ldh, float alpha, float beta, int chunk_tokens,
+                         float* H, int64_t ldh, float alpha, float beta, int chunk_tokens, int variant,
                          void* ws, size_t ws_bytes, void* stream);
 /* Plain CUDA-core fp32 X^T X with the same contract (test cross-check for the tensor path;
  * never called by the Python package). */

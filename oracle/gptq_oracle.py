@@ -211,11 +211,13 @@ class FasterquantResult:
     final_scale: torch.Tensor       # quantizer.scale after the run ([R,1]; last group)
     final_zero: torch.Tensor
     U: torch.Tensor = field(repr=False, default=None)   # upper factor of H^-1 (gptq.py:179)
+    margin: torch.Tensor = field(repr=False, default=None)   # [R,K] distance of w/scale from the nearest rounding
+                                                             # boundary (x.5) when the column was quantized (keep_margin)
 
 
 def fasterquant(W: torch.Tensor, H: torch.Tensor, qp: QParams, blocksize: int = 128,
                 percdamp: float = .01, groupsize: int = -1, actorder: bool = False,
-                static_groups: bool = False, keep_U: bool = False) -> FasterquantResult:
+                static_groups: bool = False, keep_U: bool = False, keep_margin: bool = False) -> FasterquantResult:
     """gptq.py:126-305, standard branch (lut_quant = non_linear_quant = columnwise = False).
 
     ``W`` [R,K] (any float dtype), ``H`` [K,K] fp32 as left by add_batch.  Both are cloned.
@@ -247,6 +249,7 @@ def fasterquant(W: torch.Tensor, H: torch.Tensor, qp: QParams, blocksize: int = 
     Losses = torch.zeros_like(W)
     Q = torch.zeros_like(W)
     C = torch.zeros_like(W)
+    M = torch.full_like(W, 0.5) if keep_margin else None     # test instrumentation only; not part of the reference
 
     Hinv = hinv_upper(H, percdamp)                          # gptq.py:174-180
     if not qp.ready():                                      # gptq.py:181-185
@@ -290,6 +293,9 @@ def fasterquant(W: torch.Tensor, H: torch.Tensor, qp: QParams, blocksize: int = 
             q = quantize(w.unsqueeze(1), cur.scale, cur.zero, maxq).flatten()   # gptq.py:262-264
             if maxq > 0:
                 C1[:, i] = quantize_codes(w.unsqueeze(1), cur.scale, cur.zero, maxq).flatten()
+                if keep_margin:
+                    t = (w.unsqueeze(1) / cur.scale).flatten()
+                    M[:, i1 + i] = torch.abs(t - torch.floor(t) - 0.5)
             Q1[:, i] = q
             Losses1[:, i] = (w - q) ** 2 / d ** 2           # gptq.py:267
             err1 = (w - q) / d                              # gptq.py:269
@@ -305,11 +311,13 @@ def fasterquant(W: torch.Tensor, H: torch.Tensor, qp: QParams, blocksize: int = 
         Q = Q[:, invperm]
         C = C[:, invperm]
         g_idx = g_idx_perm[invperm]
+        if M is not None:
+            M = M[:, invperm]
     else:
         g_idx = g_idx_perm
     return FasterquantResult(Q=Q, codes=C.to(torch.uint8), scales=scales, zeros=zeros, g_idx=g_idx,
                              perm=perm, error=error, final_scale=cur.scale.clone(),
-                             final_zero=cur.zero.clone(), U=Hinv if keep_U else None)
+                             final_zero=cur.zero.clone(), U=Hinv if keep_U else None, margin=M)
 
 
 # --------------------------------------------------------------------------------------
@@ -442,6 +450,32 @@ def recon_error(W: torch.Tensor, Q: torch.Tensor, H: torch.Tensor) -> float:
     """||W X - Q X||^2 (up to the 2/N factor in H) = tr(dW H dW^T)."""
     d = (W.double() - Q.double())
     return float(torch.einsum("ik,kl,il->", d, H.double(), d))
+
+
+def classify_mismatches(codes: torch.Tensor, ref: "FasterquantResult", tol: float) -> dict:
+    """Rounding-tie classifier for a run compared with the oracle run `ref` (which must carry `margin`).
+
+    Rows are independent recurrences (gptq.py:191-276 acts row-wise), and inside a row everything after the first
+    differing column legitimately differs (the error feedback of that column is different).  So a row's mismatches are
+    explained iff its FIRST differing column, in processing order (act-order permutation), was a rounding tie for the
+    oracle: |frac(w/scale) - 0.5| < tol, i.e. a perturbation of w/scale below `tol` flips round().  Returns counts;
+    `unexplained_rows` must be 0 and `mismatch_outside_tie_rows` (entries differing in rows without a tie) is then 0 too.
+    """
+    assert ref.margin is not None, "run the oracle with keep_margin=True"
+    a, b, m = codes.cpu(), ref.codes, ref.margin
+    if ref.perm is not None:                      # original order -> processing order
+        a, b, m = a[:, ref.perm], b[:, ref.perm], m[:, ref.perm]
+    diff = a != b
+    bad_rows = torch.nonzero(diff.any(dim=1)).flatten()
+    first = diff[bad_rows].to(torch.uint8).argmax(dim=1)
+    fm = m[bad_rows, first] if len(bad_rows) else torch.zeros(0)
+    tie = fm < tol
+    unexplained = bad_rows[~tie]
+    outside = int(diff[unexplained].sum()) if len(unexplained) else 0
+    return dict(mismatch=float(diff.double().mean()), rows_bad=int(len(bad_rows)), tie_rows=int(tie.sum()),
+                unexplained_rows=int(len(unexplained)), mismatch_outside_tie_rows=outside,
+                max_first_margin=float(fm.max()) if len(fm) else 0.0,
+                first_margins=[float(x) for x in fm[:8]], tol=tol)
 
 
 def code_agreement(a: torch.Tensor, b: torch.Tensor) -> float:

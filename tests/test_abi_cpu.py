@@ -41,7 +41,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_abi_version_and_error_string(lib):
     L = lib.load()
-    assert L.gptq_b200_abi_version() == 2
+    assert L.gptq_b200_abi_version() == lib.ABI_VERSION == 3
     # argument validation happens before any CUDA call, so it is testable without a GPU
     rc = L.gptq_b200_pack_codes(0, 4, 32, 32, 3, 0, 0)
     assert rc == -1

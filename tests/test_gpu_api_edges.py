@@ -50,9 +50,10 @@ def test_odd_shapes_match_oracle(R, K):
     assert O.rel_fro(g.H.cpu(), st.H) < 1e-5
     g.H = st.H.to(DEV).clone()                                            # identical H -> exact comparison of the solver
     _quiet(g.fasterquant, groupsize=32 if K >= 64 else -1)
-    ref = O.fasterquant(W, st.H, O.QParams(bits=4), groupsize=32 if K >= 64 else -1)
-    bad_rows = int((g.codes.cpu() != ref.codes).any(dim=1).sum())
-    assert bad_rows <= 1, bad_rows                                        # at most one rounding-tie flip
+    ref = O.fasterquant(W, st.H, O.QParams(bits=4), groupsize=32 if K >= 64 else -1, keep_margin=True)
+    cls = O.classify_mismatches(g.codes, ref, 2.0 ** -10)                # identical H: rows may differ only from a rounding tie on
+    bad_rows = cls["rows_bad"]
+    assert cls["unexplained_rows"] == 0 and bad_rows <= 1, cls
     if bad_rows == 0:
         # identical codes; with dynamic groups the group scale is fitted to the lazily UPDATED weights (gptq.py:255), whose
         # last fp32 bits depend on the summation order of the update GEMM, so the dequantised fp16 value may differ by an ulp

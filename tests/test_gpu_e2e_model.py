@@ -54,16 +54,22 @@ def test_sequential_quantization_matches_oracle(kind, qa):
     ppl_ref = S.eval_ppl(m_ref, evalt, dev, seqlen)
     # Codes are comparable only where both runs saw IDENTICAL inputs, i.e. in decoder layer 0: from layer 1 on each run
     # calibrates on the outputs of its own quantized layers, so one legitimate rounding-tie flip upstream changes H.
-    tot = mism = tot_all = mism_all = rows_bad = 0
+    # Every differing row of layer 0 must start at a rounding tie of the oracle run (O.classify_mismatches); within the
+    # layer, a tie flip in an earlier subset perturbs the later subsets' Hessians (true-sequential), hence the gpu_H
+    # tolerance of tests/test_gpu_headline.py.
+    from oracle import gptq_oracle as O
+    tot = mism = tot_all = mism_all = rows_bad = unexplained = 0
     for k in ex_ref:
         a, b = ex_gpu[k]["codes"].cpu(), ex_ref[k]["codes"]
         tot_all += a.numel()
         mism_all += int((a != b).sum())
         if ".layers.0." in k:
+            cls = O.classify_mismatches(a, ex_ref[k]["oracle_result"], 2.0 ** -8)
             tot += a.numel()
             mism += int((a != b).sum())
-            rows_bad += int((a != b).any(dim=1).sum())
+            rows_bad += cls["rows_bad"]
+            unexplained += cls["unexplained_rows"]
     print(f"  [metric] e2e {kind} {qa}: ppl fp16 {ppl_fp:.3f} gpu {ppl_gpu:.3f} ref {ppl_ref:.3f} "
-          f"layer-0 code mismatch {mism / tot:.2e} ({rows_bad} rows); all layers {mism_all / tot_all:.2e}")
+          f"layer-0 code mismatch {mism / tot:.2e} ({rows_bad} rows, {unexplained} not at a rounding tie); all layers {mism_all / tot_all:.2e}")
     assert abs(ppl_gpu - ppl_ref) <= 5e-3 * ppl_ref
-    assert mism / tot <= 1e-3 or rows_bad <= 3
+    assert unexplained == 0

@@ -27,6 +27,11 @@ def _log(**kw):
     print("  [metric] " + json.dumps(kw))
 
 
+# |frac(w/scale) - 0.5| below which a rounding flip between the CUDA path and the oracle counts as a tie (see
+# tests/test_gpu_headline.py): same_H = both solvers see the oracle's Hessian, gpu_H = H from the tcgen05 syrk
+TIE_TOL = {"same_H": 2.0 ** -10, "gpu_H": 2.0 ** -8}
+
+
 # ------------------------------------------------------------------------------------------ pack
 @pytest.mark.parametrize("bits", [2, 3, 4, 8])
 @pytest.mark.parametrize("R,K", [(40, 96), (64, 128), (200, 352), (1024, 1024)])
@@ -80,9 +85,20 @@ def test_quantizer_matches_reference(golden_quantizer):
         z_ref = torch.from_numpy(z[c["name"] + "/zero"])
         assert q.scale.shape == s_ref.shape, c["name"]
         if c.get("mse", False):
-            # |q-x|^2.4 uses CUDA powf vs torch CPU pow: the argmin may move at near-ties
-            frac = float((q.scale.cpu() == s_ref).float().mean())
-            assert frac >= 0.8, (c["name"], frac)
+            # |q-x|^2.4 uses CUDA powf vs torch CPU pow: the argmin over the 80 shrink steps may move between two steps
+            # whose errors are equal to rounding.  Every row whose scale differs must be such a near-tie: the error of the
+            # GPU's choice, recomputed with the oracle's arithmetic, is within 1e-5 of the error of the oracle's choice.
+            maxq = 2 ** c["bits"] - 1
+            xr = x.cpu().float().flatten(1) if c["perchannel"] else x.cpu().float().flatten().unsqueeze(0)
+            def _err(sc, zr):
+                sc, zr = sc.cpu().reshape(-1, 1)[: xr.shape[0]], zr.cpu().reshape(-1, 1)[: xr.shape[0]]
+                qx = O.quantize(xr, sc, zr, maxq)
+                return ((qx - xr).abs().double() ** 2.4).sum(1)
+            e_gpu, e_ref = _err(q.scale, q.zero), _err(s_ref, z_ref)
+            differs = (q.scale.cpu().reshape(-1)[: xr.shape[0]] != s_ref.reshape(-1)[: xr.shape[0]])
+            worst = float(((e_gpu - e_ref).abs() / e_ref.clamp_min(1e-30))[differs].max()) if differs.any() else 0.0
+            _log(test="quantizer_mse", case=c["name"], rows_differing=int(differs.sum()), worst_rel_err_gap=worst)
+            assert worst <= 1e-5, (c["name"], worst)
             continue
         assert torch.equal(q.scale.cpu(), s_ref), c["name"]
         assert torch.equal(q.zero.cpu(), z_ref), c["name"]
@@ -179,11 +195,12 @@ def _syrk(X, K, kind, alpha=1.0, beta=0.0, H0=None, chunk=0):
     lib = _lib.load()
     T = X.shape[0]
     H = torch.zeros((K, K), device=DEV) if H0 is None else H0.clone()
-    if kind == "tc":
-        n = lib.gptq_b200_syrk_workspace_bytes(K, T)
+    if kind in ("tc", "tc1", "tc2"):
+        variant = {"tc": _lib.SYRK_AUTO, "tc1": _lib.SYRK_CTA1, "tc2": _lib.SYRK_CTA2}[kind]
+        n = lib.gptq_b200_syrk_workspace_bytes(K, T, variant)
         ws = torch.empty(max(n, 16), dtype=torch.uint8, device=DEV)
         _lib.check(lib.gptq_b200_syrk_accum(X.data_ptr(), _lib.dt(X), T, K, X.stride(0), H.data_ptr(), K, alpha, beta, chunk,
-                                            ws.data_ptr(), n, _lib.stream()), "syrk_accum")
+                                            variant, ws.data_ptr(), n, _lib.stream()), "syrk_accum")
     else:
         _lib.check(lib.gptq_b200_syrk_accum_simt(X.data_ptr(), _lib.dt(X), T, K, X.stride(0), H.data_ptr(), K, alpha, beta,
                                                  _lib.stream()), "syrk_simt")
@@ -198,17 +215,39 @@ def _acts(T, K, seed, dtype):
     return (torch.randn(T, K, generator=g) * chan).to(dtype)
 
 
+@pytest.mark.parametrize("kind", ["tc1", "tc2"])       # cta_group::1 (M128 x N256 per SM) and cta_group::2 (M256 x N256 per pair)
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("T,K", [(64, 64), (100, 200), (2048, 256), (2048, 768), (8192, 1024), (4096, 2048), (333, 136)])
-def test_syrk_tc_vs_fp64(T, K, dtype):
+@pytest.mark.parametrize("T,K", [(64, 64), (100, 200), (2048, 256), (2048, 768), (8192, 1024), (4096, 2048), (333, 136),
+                                 (1000, 520), (640, 2312)])
+def test_syrk_tc_vs_fp64(T, K, dtype, kind):
     X = _acts(T, K, T + K, dtype)
     want = X.double().t() @ X.double()
-    got = _syrk(X.to(DEV), K, "tc")
+    got = _syrk(X.to(DEV), K, kind)
     err = O.rel_fro(got.cpu(), want)
     sim = O.rel_fro(_syrk(X.to(DEV), K, "simt").cpu(), want)
-    _log(test="syrk_tc", T=T, K=K, dtype=str(dtype), rel_tc=err, rel_simt=sim)
+    _log(test="syrk_tc", kind=kind, T=T, K=K, dtype=str(dtype), rel_tc=err, rel_simt=sim)
     assert sim < 1e-5
     assert err < 1e-5
+    assert torch.equal(got, got.t())
+
+
+def test_syrk_variants_agree_llama_shape():
+    """Both tensor-core kernels on one staging window of the headline shape (16 samples x 2048 tokens, K = 4096): same H up
+    to the summation order inside the tensor core, and a checksum property that does not need an fp64 K x K product:
+    1^T H 1 = sum_t (sum_c x_tc)^2."""
+    T, K = 32768, 4096
+    g = torch.Generator(device="cuda").manual_seed(3)
+    X = (torch.randn(T, K, device=DEV, generator=g) * torch.exp(0.5 * torch.randn(K, device=DEV, generator=g))).half()
+    H1 = _syrk(X, K, "tc1")
+    H2 = _syrk(X, K, "tc2")
+    rel = float(torch.linalg.norm(H1 - H2) / torch.linalg.norm(H1))
+    want = float((X.double().sum(1) ** 2).sum())
+    got = float(H2.double().sum())
+    tr = float((X.double() ** 2).sum())
+    _log(test="syrk_variants", rel_1_vs_2=rel, checksum_rel=abs(got - want) / abs(want), trace_rel=abs(float(H2.diagonal().double().sum()) - tr) / tr)
+    assert rel < 2e-6
+    assert abs(got - want) <= 1e-5 * abs(tr)
+    assert abs(float(H2.diagonal().double().sum()) - tr) <= 1e-5 * tr
 
 
 def test_syrk_tc_alpha_beta_and_chunks():
@@ -218,10 +257,11 @@ def test_syrk_tc_alpha_beta_and_chunks():
     H0 = (H0 + H0.t()).to(DEV)
     want = 0.5 * H0.cpu().double() + 0.25 * (X.double().t() @ X.double())
     for chunk in (0, 64, 512, 4096):
-        got = _syrk(X.to(DEV), K, "tc", alpha=0.25, beta=0.5, H0=H0, chunk=chunk)
-        err = O.rel_fro(got.cpu(), want)
-        _log(test="syrk_tc_alpha_beta", chunk=chunk, rel=err)
-        assert err < 1e-5
+        for kind in ("tc1", "tc2"):
+            got = _syrk(X.to(DEV), K, kind, alpha=0.25, beta=0.5, H0=H0, chunk=chunk)
+            err = O.rel_fro(got.cpu(), want)
+            _log(test="syrk_tc_alpha_beta", kind=kind, chunk=chunk, rel=err)
+            assert err < 1e-5
 
 
 def test_syrk_accumulation_bias_long():
@@ -321,19 +361,22 @@ def test_fasterquant_vs_oracle_medium(cfg):
         O.add_batch(st, b)
     qp = O.QParams(bits=cfg["bits"])
     ref = O.fasterquant(W16, st.H, qp, groupsize=cfg.get("groupsize", -1), actorder=cfg.get("actorder", False),
-                        static_groups=cfg.get("static_groups", False))
+                        static_groups=cfg.get("static_groups", False), keep_margin=True)
     for mode in ("same_H", "gpu_H"):
         lin, g = _run_gptq(W16, batches, cfg, H_override=st.H if mode == "same_H" else None)
-        mism_codes = 1.0 - O.code_agreement(g.codes.cpu(), ref.codes)
+        # rounding-tie classifier (oracle/gptq_oracle.py): a row may differ only from a column on where the oracle's
+        # w/scale sat within TIE_TOL of a rounding boundary; everything outside such rows must be identical
+        cls = O.classify_mismatches(g.codes, ref, TIE_TOL[mode])
         mism_q = float((lin.weight.data.cpu() != ref.Q.half()).double().mean())
         rel_err = abs(g.error - ref.error) / abs(ref.error)
         rec_gpu = O.recon_error(W16.float(), lin.weight.data.cpu().float(), st.H)
         rec_ref = O.recon_error(W16.float(), ref.Q, st.H)
-        _log(test="fasterquant_medium", case=cfg["name"], H=mode, code_mismatch=mism_codes, q_mismatch=mism_q,
-             err_gpu=g.error, err_ref=ref.error, recon_gpu=rec_gpu, recon_ref=rec_ref)
-        # a rounding-tie flip legitimately diverges the REST of that row; with few rows one such row exceeds 0.1 %
-        rows_bad = int((g.codes.cpu() != ref.codes).any(dim=1).sum())
-        assert mism_codes <= 1e-3 or rows_bad <= 2, (mode, mism_codes, rows_bad)
+        _log(test="fasterquant_medium", case=cfg["name"], H=mode, q_mismatch=mism_q, err_gpu=g.error, err_ref=ref.error,
+             recon_gpu=rec_gpu, recon_ref=rec_ref, **cls)
+        assert cls["unexplained_rows"] == 0, (mode, cls)
+        # at this reduced width one tie row alone is > 0.1 % of the entries, so the 99.9 % gate is applied to the full
+        # shapes in test_gpu_headline.py; here ties must stay rare
+        assert cls["tie_rows"] <= max(2, R // 100), (mode, cls)
         assert rel_err <= 1e-2, mode
         assert abs(rec_gpu - rec_ref) <= 1e-2 * rec_ref, mode
         if cfg.get("actorder", False) and mode == "same_H":

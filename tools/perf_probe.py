@@ -29,21 +29,21 @@ def timeit(fn, warm=2, iters=5):
     return min(ts), sum(ts) / len(ts)
 
 
-def probe_syrk(K, T, chunk=0, dtype=torch.float16):
+def probe_syrk(K, T, chunk=0, dtype=torch.float16, variant=0, iters=5):
     X = (torch.randn(T, K, device=DEV) * 0.5).to(dtype)
     H = torch.zeros(K, K, device=DEV)
-    n = lib.gptq_b200_syrk_workspace_bytes(K, T)
+    n = lib.gptq_b200_syrk_workspace_bytes(K, T, variant)
     ws = torch.empty(max(n, 16), dtype=torch.uint8, device=DEV)
 
     def run():
-        _lib.check(lib.gptq_b200_syrk_accum(X.data_ptr(), _lib.dt(X), T, K, K, H.data_ptr(), K, 1.0, 1.0, chunk, ws.data_ptr(), n,
-                                            _lib.stream()), "syrk")
-    best, avg = timeit(run)
+        _lib.check(lib.gptq_b200_syrk_accum(X.data_ptr(), _lib.dt(X), T, K, K, H.data_ptr(), K, 1.0, 1.0, chunk, variant,
+                                            ws.data_ptr(), n, _lib.stream()), "syrk")
+    best, avg = timeit(run, iters=iters)
     nbm, nbn = (K + 127) // 128, (K + 255) // 256
     tiles = sum(nbm - 2 * j for j in range(nbn))
-    issued = 2.0 * tiles * 128 * 256 * T
+    issued = 2.0 * tiles * 128 * 256 * T          # = 256x256 pair tiles with bi >= bj: the same count for both kernels
     dense = 2.0 * K * K * T
-    print(json.dumps(dict(op="syrk", K=K, T=T, chunk=chunk, ms=best, ms_avg=avg, issued_tflops=issued / best / 1e9,
+    print(json.dumps(dict(op="syrk", variant=variant, K=K, T=T, chunk=chunk, ms=best, ms_avg=avg, issued_tflops=issued / best / 1e9,
                           dense_equiv_tflops=dense / best / 1e9)))
 
 
@@ -125,10 +125,18 @@ def probe_sgemm(M, N, Kd):
 if __name__ == "__main__":
     what = sys.argv[1:] or ["syrk", "hinv", "colloop", "pack", "sgemm"]
     if "syrk" in what:
-        for K, T in ((4096, 32768), (4096, 2048), (11008, 32768), (768, 32768), (2048, 32768)):
-            probe_syrk(K, T)
+        for variant in (1, 2):
+            for K, T in ((4096, 32768), (4096, 2048), (11008, 32768), (768, 32768), (2048, 32768)):
+                probe_syrk(K, T, variant=variant)
         for chunk in (64, 128, 256, 1024, 4096):
             probe_syrk(4096, 32768, chunk)
+    if "syrk2" in what:          # the two headline launch shapes, both kernels, interleaved (same clocks / power state)
+        for rep in range(2):
+            for K in (4096, 11008):
+                for variant in (1, 2):
+                    probe_syrk(K, 32768, variant=variant, iters=10)
+        for chunk in (256, 1024, 2048):
+            probe_syrk(4096, 32768, chunk, variant=2, iters=10)
     if "sgemm" in what:
         probe_sgemm(4096, 4096, 4096)
         probe_sgemm(4096, 4096, 128)
