@@ -1,27 +1,35 @@
 #!/usr/bin/env python
 """Benchmark of the GPTQ layer-wise quantization hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference|reference-cuda]
+                    [--config llama7b|opt125m|opt1.3b|bloom7b1|opt66b-layer] [--workload layer|model]
 
-Workload (BASELINE.json configs[2], the configuration the metric is quoted on): ONE Llama-2-7B
-decoder layer -- q,k,v,o 4096x4096, gate,up 11008x4096, down 4096x11008 -- quantized with GPTQ
-4-bit, groupsize 128, act-order, static groups, true-sequential subset order, from 128 x 2048
-synthetic calibration tokens (random-init fp16 weights N(0, 0.02^2), activations N(0,1) x per-channel
-exp(0.5 z)).  A step = the whole hot path for that layer through the reference-facing
-Python API: 128 add_batch calls per linear (Hessian), 7 fasterquant calls, 7 packs.
-Whole-model time = 32 x step.
+Default workload (BASELINE.json configs[2], the configuration the metric is quoted on): ONE Llama-2-7B decoder layer --
+q,k,v,o 4096x4096, gate,up 11008x4096, down 4096x11008 -- quantized with GPTQ 4-bit, groupsize 128, act-order, static
+groups, true-sequential subset order, from 128 x 2048 synthetic calibration tokens (random-init fp16 weights
+N(0, 0.02^2), activations N(0,1) x per-channel exp(0.5 z)).  A step = the whole hot path for that layer through
+the reference-facing Python API: 128 add_batch calls per linear (Hessian), one fasterquant and one pack per linear.
+`--config` selects the decoder layer of another BASELINE config (same definition of a step).
 
 `value`  : quantized weights per second, inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`    : same metric with every step's activations and weights starting in PINNED HOST memory
-           (H2D copies inside the timed region) and the packed result read back to the host.
-N > 1    : strong scaling of the same layer: calibration samples sharded (one NCCL all-reduce of each
-           partial Hessian), W rows sharded (one all-gather of weights/codes/scales/zeros).
---impl reference : the reference algorithm on the host CPU (oracle/gptq_oracle.py, a torch-CPU
-           restatement pinned bit-exact to the reference), bounded sample per step, extrapolated.
+`e2e`    : same metric with every step's activations and weights starting in PINNED HOST memory (H2D copies inside the
+           timed region) and the packed result read back to the host.
+N > 1    : strong scaling of the same layer: calibration samples sharded (one all-reduce of each partial Hessian's lower
+           triangle), W rows sharded (one coalesced all-gather of weights/codes/scales/zeros); a `parity` object compares
+           the sharded result of one linear with the single-GPU result (outside the timed region).
+--impl reference      : the UNMODIFIED reference (baseline/_ref, see baseline/install_reference.py) on the host CPU with
+           all host threads; each step is a bounded sample of the layer; the layer time is assembled from the measured
+           unit costs (stated in `cpu_baseline.sample`).  Falls back to the oracle port if baseline/_ref is absent.
+--impl reference-cuda : the same unmodified reference classes with CUDA tensors on the same GPU (cuBLAS fp32 sgemm,
+           cuSOLVER, eager column loop; TF32 off) -- the like-for-like GPU baseline, whole layer, no sampling.
+--workload model      : whole-model quantization through gptq_b200.sequential (random-init HF model; SURVEY 8d definition
+           of "whole-model quantize time"), see run_model().
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
+import io
 import json
 import os
 import statistics
@@ -35,24 +43,61 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-HID, INTER, NSAMPLES, SEQ = 4096, 11008, 128, 2048
-# (name, rows, cols, activation-id); activation 0 = attn input, 1 = o_proj input, 2 = mlp input, 3 = down input
-LINEARS = [("k_proj", HID, HID, 0), ("v_proj", HID, HID, 0), ("q_proj", HID, HID, 0), ("o_proj", HID, HID, 1),
-           ("up_proj", INTER, HID, 2), ("gate_proj", INTER, HID, 2), ("down_proj", HID, INTER, 3)]
-SUBSETS = [[0, 1, 2], [3], [4, 5], [6]]                       # llama.py:98-103 true-sequential order
-ACT_K = [HID, HID, HID, INTER]
-LAYER_WEIGHTS = sum(r * c for _, r, c, _ in LINEARS)
-N_LAYERS = 32
-GPTQ_KW = dict(blocksize=128, percdamp=.01, groupsize=128, actorder=True, static_groups=True)
-WBITS = 4
+NSAMPLES, SEQ = 128, 2048
+
+
+def _layer(title, linears, subsets, act_k, n_layers, wbits, gptq, pack="codes", note=""):
+    return dict(title=title, linears=linears, subsets=subsets, act_k=act_k, n_layers=n_layers, wbits=wbits, gptq=gptq,
+                pack=pack, note=note, weights=sum(r * c for _, r, c, _ in linears))
+
+
+def _opt(h, f):
+    return [("k_proj", h, h, 0), ("v_proj", h, h, 0), ("q_proj", h, h, 0), ("out_proj", h, h, 1), ("fc1", f, h, 2), ("fc2", h, f, 3)]
+
+
+# (name, rows, cols, activation-id): linears with the same activation-id are hooked on the same tensor (share one Hessian)
+WORKLOADS = {
+    # configs[2] -- llama.py:98-103 true-sequential subset order
+    "llama7b": _layer("Llama-2-7B decoder layer (q,k,v,o 4096x4096; gate,up 11008x4096; down 4096x11008), GPTQ 4-bit g128 "
+                      "act-order static-groups true-sequential",
+                      [("k_proj", 4096, 4096, 0), ("v_proj", 4096, 4096, 0), ("q_proj", 4096, 4096, 0), ("o_proj", 4096, 4096, 1),
+                       ("up_proj", 11008, 4096, 2), ("gate_proj", 11008, 4096, 2), ("down_proj", 4096, 11008, 3)],
+                      [[0, 1, 2], [3], [4, 5], [6]], [4096, 4096, 4096, 11008], 32, 4,
+                      dict(blocksize=128, percdamp=.01, groupsize=128, actorder=True, static_groups=True)),
+    # configs[0] -- opt.py:109-187: all six linears of a layer are hooked in ONE forward (no true-sequential)
+    "opt125m": _layer("OPT-125m decoder layer (q,k,v,out 768x768; fc1 3072x768; fc2 768x3072), GPTQ 4-bit per-channel",
+                      _opt(768, 3072), [[0, 1, 2, 3, 4, 5]], [768, 768, 768, 3072], 12, 4,
+                      dict(blocksize=128, percdamp=.01, groupsize=-1, actorder=False, static_groups=True),
+                      note="static_groups=True is opt.py's default (opt.py:584-587), a no-op at groupsize -1"),
+    # configs[1] -- packed through the fp16-weights entry point Quant3Linear.pack(linear, scales, zeros) (quant.py:152-187)
+    "opt1.3b": _layer("OPT-1.3b decoder layer (q,k,v,out 2048x2048; fc1 8192x2048; fc2 2048x8192), GPTQ 3-bit g128 + "
+                      "Quant3Linear.pack", _opt(2048, 8192), [[0, 1, 2, 3, 4, 5]], [2048, 2048, 2048, 8192], 24, 3,
+                      dict(blocksize=128, percdamp=.01, groupsize=128, actorder=False, static_groups=True), pack="linear",
+                      note="static_groups=True is opt.py's default (opt.py:584-587)"),
+    # configs[3] -- bloom.py:93-170, dynamic groups (stale-W group fit, gptq.py:253-255)
+    "bloom7b1": _layer("BLOOM-7b1 decoder layer (query_key_value 12288x4096; dense 4096x4096; dense_h_to_4h 16384x4096; "
+                       "dense_4h_to_h 4096x16384), GPTQ 2-bit g64",
+                       [("query_key_value", 12288, 4096, 0), ("dense", 4096, 4096, 1), ("dense_h_to_4h", 16384, 4096, 2),
+                        ("dense_4h_to_h", 4096, 16384, 3)], [[0, 1, 2, 3]], [4096, 4096, 4096, 16384], 30, 2,
+                       dict(blocksize=128, percdamp=.01, groupsize=64, actorder=False, static_groups=False)),
+    # configs[4] -- one decoder layer resident at a time
+    "opt66b-layer": _layer("OPT-66B decoder layer (q,k,v,out 9216x9216; fc1 36864x9216; fc2 9216x36864), GPTQ 3-bit act-order",
+                           _opt(9216, 36864), [[0, 1, 2, 3, 4, 5]], [9216, 9216, 9216, 36864], 64, 3,
+                           dict(blocksize=128, percdamp=.01, groupsize=-1, actorder=True, static_groups=True),
+                           note="static_groups=True is opt.py's default, a no-op at groupsize -1"),
+}
 
 
 def syrk_traffic(prof):
-    """Launch-weighted DRAM bytes per syrk launch of the timed region, from the committed ncu capture
-    (profiles/r01_syrk_traffic.json: per launch shape).  None if a launch shape was not captured."""
-    path = os.path.join(ROOT, "profiles", "r01_syrk_traffic.json")
-    if not os.path.exists(path):
-        return None
+    """Launch-weighted DRAM bytes per Hessian-kernel launch of the timed region, from the committed ncu capture
+    (profiles/*_syrk_traffic.json: per launch shape).  None if a launch shape was not captured."""
+    path = None
+    for name in ("r02_syrk_traffic.json", "r01_syrk_traffic.json"):
+        if os.path.exists(os.path.join(ROOT, "profiles", name)):
+            path = os.path.join(ROOT, "profiles", name)
+            break
+    if path is None:
+        return None, None
     with open(path) as f:
         shapes = json.load(f)["launch_shapes"]
     tot, n = 0.0, 0
@@ -61,10 +106,10 @@ def syrk_traffic(prof):
             continue
         ent = shapes.get("K%d_T%d" % meta) if meta else None
         if ent is None:
-            return None
+            return None, os.path.basename(path)
         tot += ent["dram_read_bytes"] + ent["dram_write_bytes"]
         n += 1
-    return tot / n if n else None
+    return (tot / n if n else None), os.path.basename(path)
 
 
 def peaks():
@@ -113,90 +158,229 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ reference arm (CPU)
-def cpu_reference_sample(threads=None):
-    """Bounded sample of the workload on the host CPU with the oracle port; returns extrapolated layer seconds."""
-    from oracle import gptq_oracle as O
-    if threads:
-        torch.set_num_threads(threads)
-    g = torch.Generator().manual_seed(0)
-    K = HID
-    chan = torch.exp(0.5 * torch.randn(K, generator=g))
-    x = (torch.randn(1, SEQ, K, generator=g) * chan).half()
-    st = O.HessianState(K)
-    t0 = time.perf_counter()
-    O.add_batch(st, x)                                       # gptq.py:38-65, one of the 128 samples
-    t_h = time.perf_counter() - t0
-    # fasterquant on a 512-row slice of q_proj (the chain is full size; the loop is row-proportional)
-    RS = 512
-    W = (torch.randn(RS, K, generator=g) * 0.02).half()
-    H = st.H + torch.eye(K) * 1e-3
-    t0 = time.perf_counter()
-    H2 = H.clone()
-    O.hinv_upper(H2, 0.01)
-    t_chain = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    O.fasterquant(W, H, O.QParams(bits=WBITS), **{k: v for k, v in GPTQ_KW.items()})
-    t_fq = time.perf_counter() - t0
-    t_loop = max(t_fq - t_chain, 1e-6)                       # row-proportional part for RS rows, K=4096
-    # extrapolation to the full layer (stated in cpu_baseline.sample):
-    #   Hessian: dense fp32 sgemm, time ~ K^2 * tokens  -> 128 samples x (6 x K=4096 + 1 x K=11008)
-    #   chain:   ~ K^3                                   -> 6 x K=4096 + 1 x K=11008
-    #   loop:    ~ R * K^2                               -> per linear
-    kr = (INTER / HID)
-    t_hess = NSAMPLES * t_h * (6 + kr ** 2)
-    t_ch = t_chain * (6 + kr ** 3)
-    t_lp = sum(t_loop * (r / RS) * (c / K) ** 2 for _, r, c, _ in LINEARS)
-    total = t_hess + t_ch + t_lp
-    return dict(layer_seconds=total, hessian_seconds=t_hess, chain_seconds=t_ch, loop_seconds=t_lp,
-                measured=dict(add_batch_1sample_K4096=t_h, chain_K4096=t_chain, fasterquant_512x4096=t_fq),
-                cores=torch.get_num_threads(),
-                sample=("per step: add_batch on 1 of 128 samples (2048 tokens, K=4096) + fasterquant of a 512x4096 slice of "
-                        "q_proj (full 4096^2 inverse-Cholesky chain); extrapolated to the layer with Hessian~K^2*tokens, "
-                        "chain~K^3, loop~R*K^2"))
+def metric_name(cfg):
+    if cfg == "llama7b":
+        return "llama2_7b_gptq_4b_g128_actorder_layer_quantization_throughput"
+    return cfg.replace("-", "_").replace(".", "_") + "_gptq_layer_quantization_throughput"
+
+
+def base_line(args, wl, value, ms_per_step):
+    return {"metric": metric_name(args.config), "value": value, "unit": "Mweights/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16xf16->f32 (Hessian), f32 (solver)",
+            "data": "synthetic",
+            "config": {"workload": wl["title"] + f", {NSAMPLES}x{SEQ} calibration tokens; step = {NSAMPLES} add_batch/linear + "
+                                   f"{len(wl['linears'])} fasterquant + {len(wl['linears'])} pack; whole model = {wl['n_layers']} such layers",
+                       "weights_per_step": wl["weights"], "calibration_tokens": NSAMPLES * SEQ, "note": wl["note"],
+                       "l2": "inputs (GBs of activations per step) exceed the 126 MB L2; no explicit flush"}}
+
+
+# ------------------------------------------------------------------------------------------ reference arms
+def _reference_classes():
+    """(GPTQ class, Quantizer class, kind): the unmodified reference from baseline/_ref, else the oracle port."""
+    from baseline import reference as BR
+    if BR.available():
+        rg, rq = BR.load()
+        return rg.GPTQ, rq.Quantizer, "reference"
+    from oracle.ref_gptq import OracleGPTQ, OracleQuantizer
+    return OracleGPTQ, OracleQuantizer, "port"
+
+
+def _host_threads():
+    """All host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def _ref_gptq(GPTQcls, Qcls, W, wbits, dev="cpu"):
+    import torch.nn as nn
+    R, K = W.shape
+    lin = nn.Linear(K, R, bias=False)
+    lin.weight.data = W.to(dev)
+    lin = lin.to(dev)
+    g = GPTQcls(lin)
+    g.quantizer = Qcls()
+    g.quantizer.configure(wbits, perchannel=True, sym=False, mse=False)
+    return lin, g
+
+
+_CPU_ONCE = {}
+
+
+def cpu_reference_sample(wl):
+    """One bounded sample of the layer on the host CPU with the reference's own classes.  Measured every call: add_batch
+    on 2 of the 128 samples and one FULL fasterquant at the layer's first linear shape.  Measured once per process
+    (seconds each, reused by later steps): a 512-row fasterquant at that shape (separates the row-proportional column loop
+    from the Cholesky chain), and for every other distinct K of the layer one add_batch sample and fasterquant of two row
+    slices.  The layer time is assembled from those unit costs with the layer's own counts -- no exponent laws."""
+    GPTQcls, Qcls, kind = _reference_classes()
+    cores = _host_threads()
+    quiet = io.StringIO()
+    g0 = torch.Generator().manual_seed(0)
+    kw = {k: wl["gptq"][k] for k in ("blocksize", "percdamp", "groupsize", "actorder", "static_groups")}
+    t_wall0 = time.perf_counter()
+
+    def acts(K, n):
+        chan = torch.exp(0.5 * torch.randn(K, generator=g0))
+        return [(torch.randn(1, SEQ, K, generator=g0) * chan).half() for _ in range(n)]
+
+    def time_fq(R, K, xs):
+        W = (torch.randn(R, K, generator=g0) * 0.02).half()
+        _, g = _ref_gptq(GPTQcls, Qcls, W, wl["wbits"])
+        th = []
+        for x in xs:
+            t0 = time.perf_counter()
+            g.add_batch(x, None)
+            th.append(time.perf_counter() - t0)
+        H = g.H if not callable(getattr(g, "H", None)) else None
+        if H is not None and hasattr(H, "diagonal"):
+            H.diagonal().add_(1e-2 * float(H.diagonal().mean()))     # few samples: keep the sample's H safely PD
+        t0 = time.perf_counter()
+        with contextlib.redirect_stdout(quiet), contextlib.redirect_stderr(quiet):
+            g.fasterquant(**kw)
+        return statistics.mean(th), time.perf_counter() - t0
+
+    Ks = sorted({c for _, r, c, _ in wl["linears"]})
+    K0 = wl["linears"][0][2]
+    R0 = wl["linears"][0][1]
+    key = id(wl)
+    once = _CPU_ONCE.setdefault(key, {})
+    # every call: the first linear in full
+    x0 = acts(K0, 2)
+    t_h0, t_full0 = time_fq(R0, K0, x0)
+    if "slices" not in once:
+        sl = {}
+        rs0 = max(128, R0 // 8)
+        _, t_s = time_fq(rs0, K0, x0[:1])
+        b = max((t_full0 - t_s) / (R0 - rs0), 0.0)
+        sl[K0] = dict(a=max(t_full0 - b * R0, 0.0), b=b, t_h=None, measured={f"fasterquant_{rs0}x{K0}": t_s})
+        for K in Ks:
+            if K == K0:
+                continue
+            xs = acts(K, 1)
+            ra, rb = 128, 640
+            th, ta = time_fq(ra, K, xs)
+            _, tb = time_fq(rb, K, xs)
+            b = max((tb - ta) / (rb - ra), 0.0)
+            sl[K] = dict(a=max(ta - b * ra, 0.0), b=b, t_h=th, measured={f"add_batch_1sample_K{K}": th, f"fasterquant_{ra}x{K}": ta,
+                                                                         f"fasterquant_{rb}x{K}": tb})
+        once["slices"] = sl
+    sl = once["slices"]
+    # refresh the per-call part of the model for K0
+    b0 = sl[K0]["b"]
+    a0 = max(t_full0 - b0 * R0, 0.0)
+    t_hess = t_solve = 0.0
+    for _, r, c, _ in wl["linears"]:
+        th = t_h0 if c == K0 else sl[c]["t_h"]
+        a, b = (a0, b0) if c == K0 else (sl[c]["a"], sl[c]["b"])
+        t_hess += NSAMPLES * th
+        t_solve += a + b * r
+    measured = {f"add_batch_1sample_K{K0}": t_h0, f"fasterquant_{R0}x{K0}_full": t_full0}
+    for K in sl:
+        measured.update(sl[K]["measured"])
+    return dict(layer_seconds=t_hess + t_solve, hessian_seconds=t_hess, solve_seconds=t_solve, measured=measured, cores=cores,
+                kind=kind, sample_wall_seconds=time.perf_counter() - t_wall0,
+                sample=(f"per step: reference add_batch on 2 of {NSAMPLES} samples ({SEQ} tokens, K={K0}) + one FULL reference fasterquant "
+                        f"of {wl['linears'][0][0]} {R0}x{K0}; once per process: fasterquant of a {max(128, R0 // 8)}-row slice at K={K0} and, "
+                        f"for each other K of the layer, one add_batch sample + fasterquant of 128- and 640-row slices (chain in full); layer "
+                        f"time = sum over the layer's linears of {NSAMPLES} x add_batch(K) + chain(K) + rows x per-row loop cost(K)"))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ts = []
-    last = None
+    wl = WORKLOADS[args.config]
+    ts, walls, last = [], [], None
     for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        last = cpu_reference_sample()
+        last = cpu_reference_sample(wl)
         if i >= args.warmup:
             ts.append(last["layer_seconds"])
+            walls.append(last["sample_wall_seconds"])
     layer_s = statistics.mean(ts)
-    val = LAYER_WEIGHTS / layer_s / 1e6
-    out = base_line(args, val, layer_s * 1e3)
+    val = wl["weights"] / layer_s / 1e6
+    out = base_line(args, wl, val, statistics.mean(walls) * 1e3)
     out.update({"impl": "reference", "dtype": "f32", "scaling": "strong",
-                "cpu_baseline": {"value": val, "unit": "Mweights/s", "cores": last["cores"], "kind": "port",
-                                 "sample": last["sample"], "detail": last["measured"]},
+                "ms_per_step_note": "wall time of one bounded SAMPLE step; the layer itself takes extrapolated_layer_seconds",
+                "extrapolated_layer_seconds": layer_s,
+                "cpu_baseline": {"value": val, "unit": "Mweights/s", "cores": last["cores"], "kind": last["kind"],
+                                 "sample": last["sample"], "detail": last["measured"],
+                                 "hessian_seconds": last["hessian_seconds"], "solve_seconds": last["solve_seconds"]},
                 "e2e": {"value": val, "unit": "Mweights/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "whole_model_seconds": layer_s * N_LAYERS, "gpu_launches": 0})
+                "hot_path_seconds_x_layers": layer_s * wl["n_layers"], "gpu_launches": 0})
     print(json.dumps(out))
 
 
-def base_line(args, value, ms_per_step):
-    return {"metric": "llama2_7b_gptq_4b_g128_actorder_layer_quantization_throughput", "value": value, "unit": "Mweights/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16xf16->f32 (Hessian), f32 (solver)",
-            "data": "synthetic",
-            "config": {"workload": "Llama-2-7B decoder layer (q,k,v,o 4096x4096; gate,up 11008x4096; down 4096x11008), "
-                                   "GPTQ 4-bit g128 act-order static-groups true-sequential, 128x2048 calibration tokens; "
-                                   "step = 128 add_batch/linear + 7 fasterquant + 7 pack; whole model = 32 steps",
-                       "weights_per_step": LAYER_WEIGHTS, "calibration_tokens": NSAMPLES * SEQ,
-                       "l2": "inputs (12.2 GB of activations per step) exceed the 126 MB L2; no explicit flush"}}
+def reference_cuda_layer(wl, dev, steps, warmup):
+    """The unmodified reference classes with CUDA tensors: whole layer, every sample, every linear (no sharing, no sampling)."""
+    GPTQcls, Qcls, kind = _reference_classes()
+    acts, weights = make_inputs(wl, dev, 0, 1, host=False)
+    kw = {k: wl["gptq"][k] for k in ("blocksize", "percdamp", "groupsize", "actorder", "static_groups")}
+    quiet = io.StringIO()
+    times, hess, solve = [], [], []
+    for it in range(warmup + steps):
+        torch.cuda.synchronize()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        e[0].record()
+        t_h = t_s = 0.0
+        for subset in wl["subsets"]:
+            gs = []
+            for li in subset:
+                _, g = _ref_gptq(GPTQcls, Qcls, weights[li].clone(), wl["wbits"], dev)
+                gs.append(g)
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True); c = torch.cuda.Event(enable_timing=True)
+            a.record()
+            for j in range(NSAMPLES):
+                for li, g in zip(subset, gs):
+                    g.add_batch(acts[wl["linears"][li][3]][j].unsqueeze(0), None)
+            b.record()
+            with contextlib.redirect_stdout(quiet), contextlib.redirect_stderr(quiet):
+                for g in gs:
+                    g.fasterquant(**kw)
+                    g.free()
+            c.record()
+            torch.cuda.synchronize()
+            t_h += a.elapsed_time(b)
+            t_s += b.elapsed_time(c)
+        e[1].record()
+        torch.cuda.synchronize()
+        if it >= warmup:
+            times.append(e[0].elapsed_time(e[1])); hess.append(t_h); solve.append(t_s)
+    del acts, weights
+    torch.cuda.empty_cache()
+    ms = statistics.mean(times)
+    return dict(value=wl["weights"] / (ms / 1e3) / 1e6, unit="Mweights/s", ms_per_step=ms, hessian_ms=statistics.mean(hess),
+                solve_ms=statistics.mean(solve), steps=steps, warmup=warmup, kind=kind + " classes, CUDA tensors (cuBLAS sgemm / cuSOLVER / "
+                "eager column loop, TF32 off)", note="whole layer, all 128 samples, no sampling or extrapolation")
+
+
+def run_reference_cuda(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.config]
+    torch.cuda.set_device(0)
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    r = reference_cuda_layer(wl, torch.device("cuda", 0), steps, warmup)
+    out = base_line(args, wl, r["value"], r["ms_per_step"])
+    out.update({"impl": "reference-cuda", "dtype": "f32", "steps": steps, "warmup": warmup, "n_gpus": 1, "gpu_torch_baseline": r,
+                "e2e": {"value": None, "unit": "Mweights/s", "note": "device-resident only"}, "gpu_launches": 0,
+                "hot_path_seconds_x_layers": r["ms_per_step"] * wl["n_layers"] / 1e3})
+    print(json.dumps(out))
 
 
 # ------------------------------------------------------------------------------------------ our arm (GPU)
-def make_inputs(dev, rank, world, host=False):
+def make_inputs(wl, dev, rank, world, host=False, all_samples=False):
     """Synthetic activations for this rank's sample shard, and the layer's weights."""
     from gptq_b200.dist import sample_shard
-    mine = sample_shard(NSAMPLES, rank, world)
+    mine = list(range(NSAMPLES)) if all_samples else sample_shard(NSAMPLES, rank, world)
     acts = []
-    for a, K in enumerate(ACT_K):
+    for a, K in enumerate(wl["act_k"]):
         g = torch.Generator(device=dev).manual_seed(100 + a)
         chan = torch.exp(0.5 * torch.randn(K, device=dev, generator=g))
         if host:
@@ -210,7 +394,7 @@ def make_inputs(dev, rank, world, host=False):
         acts.append(X)
     ws = []
     gw = torch.Generator(device=dev).manual_seed(1)
-    for _, r, c, _ in LINEARS:
+    for _, r, c, _ in wl["linears"]:
         w = (torch.randn(r, c, device=dev, generator=gw) * 0.02).half()
         ws.append(w.cpu().pin_memory() if host else w)
     torch.cuda.synchronize()
@@ -244,27 +428,48 @@ def _h2d_buffers(dev, nbytes, wbytes):
     return st
 
 
-def _enqueue_subset_h2d(dev, X, wlist, slot):
+def _subset_acts(wl, subset):
+    """Distinct activation ids of a subset, in first-use order."""
+    ids = []
+    for li in subset:
+        a = wl["linears"][li][3]
+        if a not in ids:
+            ids.append(a)
+    return ids
+
+
+def _enqueue_subset_h2d(wl, dev, acts, weights, subset, slot, wrows=None):
     """Caller side of the public API when activations and weights live in pinned host memory: stream the samples of
     one subset, then its weights, into landing area `slot` on the copy stream (one event per sample, one for the
     weights).  Everything host-to-device goes through this one stream: a copy issued on the compute stream would
     queue behind the transfers already in flight and stall the kernels behind it."""
     cs = _copy_stream(dev)
-    wmax = max(sum(LINEARS[li][1] * LINEARS[li][2] for li in sub) for sub in SUBSETS) * 2
-    st = _h2d_buffers(dev, NSAMPLES * SEQ * max(ACT_K) * 2, wmax)
-    n = X.numel() * X.element_size()
-    view = st["bufs"][slot][:n].view(X.dtype).view(X.shape)
-    ready, wdev = [], []
+    ids = _subset_acts(wl, subset)
+    n_local = acts[0].shape[0]
+    amax = max(sum(n_local * SEQ * wl["act_k"][a] * 2 for a in _subset_acts(wl, sub)) for sub in wl["subsets"])
+    wmax = max(sum(wl["linears"][li][1] * wl["linears"][li][2] for li in sub) for sub in wl["subsets"]) * 2 + 4096 * len(wl["linears"])
+    st = _h2d_buffers(dev, amax, wmax)
+    views, ready, wdev = {}, [], []
     with torch.cuda.stream(cs):
         if st["consumed"][slot] is not None:
             cs.wait_event(st["consumed"][slot])           # the previous occupant of this area is done with it
-        for j in range(X.shape[0]):
-            view[j].copy_(X[j], non_blocking=True)
+        off = 0
+        for a in ids:
+            X = acts[a]
+            n = X.numel() * X.element_size()
+            views[a] = st["bufs"][slot][off:off + n].view(X.dtype).view(X.shape)
+            off += n
+        for j in range(n_local):
+            for a in ids:
+                views[a][j].copy_(acts[a][j], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
             ready.append(ev)
         off = 0
-        for w in wlist:
+        for li in subset:
+            w = weights[li]
+            if wrows is not None:                          # row-sharded solve: this rank needs its own rows only
+                w = w[wrows[li][0]:wrows[li][1]]
             nb = w.numel() * w.element_size()
             wd = st["wbufs"][slot][off:off + nb].view(w.dtype).view(w.shape)
             wd.copy_(w, non_blocking=True)
@@ -272,35 +477,29 @@ def _enqueue_subset_h2d(dev, X, wlist, slot):
             off += (nb + 255) // 256 * 256
         wev = torch.cuda.Event()
         wev.record(cs)
-    return view, ready, wdev, wev
+    return views, ready, wdev, wev
 
 
-def quantize_layer(dev, acts, weights, world, from_host, carry=None, prefetch_next=False):
-    """One step: the reference driver's per-layer flow (llama.py:97-170) over our GPTQ / Quantizer / pack."""
+def quantize_layer(wl, dev, acts, weights, world, from_host, carry=None, prefetch_next=False):
+    """One step: the reference driver's per-layer flow (llama.py:97-170 / opt.py:109-214) over our GPTQ / Quantizer / pack."""
     import torch.nn as nn
+    import gptq_b200.gptq as G
     from gptq_b200.gptq import GPTQ
-    from gptq_b200.quant import Quantizer, pack_codes
+    from gptq_b200.quant import Quantizer, QuantLinear, pack_codes
     from gptq_b200 import dist as gd
     results = []
     d2h = 0
     cur = torch.cuda.current_stream()
     pending = None
-    trace = [] if (from_host and os.environ.get("GPTQ_B200_E2E_TRACE")) else None
-
-    def mark(name, stream):
-        if trace is not None:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record(stream)
-            trace.append((name, ev))
-    mark("step start", cur)
+    subsets, linears = wl["subsets"], wl["linears"]
+    rank = int(os.environ.get("RANK", "0"))
     if from_host:
         # `carry`: the previous step already queued this step's first subset behind its own last transfer
-        pending = carry if carry is not None else _enqueue_subset_h2d(
-            dev, acts[LINEARS[SUBSETS[0][0]][3]], [weights[li] for li in SUBSETS[0]], 0)
-    for si, subset in enumerate(SUBSETS):
+        pending = carry if carry is not None else _enqueue_subset_h2d(wl, dev, acts, weights, subsets[0], 0)
+    for si, subset in enumerate(subsets):
         gs = []
         for li in subset:
-            name, r, c, a = LINEARS[li]
+            name, r, c, a = linears[li]
             lin = nn.Linear(c, r, bias=False, device="meta")
             lin.to_empty(device=dev)
             lin = lin.half()
@@ -308,72 +507,120 @@ def quantize_layer(dev, acts, weights, world, from_host, carry=None, prefetch_ne
                 lin.weight.data = weights[li].clone()
             g = GPTQ(lin)
             g.quantizer = Quantizer()
-            g.quantizer.configure(WBITS, perchannel=True, sym=False, mse=False)
+            g.quantizer.configure(wl["wbits"], perchannel=True, sym=False, mse=False)
             gs.append(g)
-        X = acts[LINEARS[subset[0]][3]]
+        n_local = acts[0].shape[0]
         if from_host:
             # the H2D stream runs one subset ahead of the compute stream (while this subset's Hessians, chain and
             # column loops run, the next subset's samples are already landing in the other buffer)
-            Xd, ready, wdev, wev = pending
-            if si == 0:
-                mark("h2d subset 0 done", _copy_stream(dev))
-            if si + 1 < len(SUBSETS) or prefetch_next:      # the upload keeps running one subset ahead, across steps too
-                nxt = SUBSETS[(si + 1) % len(SUBSETS)]
-                pending = _enqueue_subset_h2d(dev, acts[LINEARS[nxt[0]][3]], [weights[li] for li in nxt], (si + 1) & 1)
-                mark(f"h2d subset {(si + 1) % len(SUBSETS)} done", _copy_stream(dev))
+            views, ready, wdev, wev = pending
+            if si + 1 < len(subsets) or prefetch_next:      # the upload keeps running one subset ahead, across steps too
+                nxt = subsets[(si + 1) % len(subsets)]
+                pending = _enqueue_subset_h2d(wl, dev, acts, weights, nxt, (si + 1) & 1)
             else:
                 pending = None
-            for j in range(Xd.shape[0]):
+            for j in range(n_local):
                 cur.wait_event(ready[j])
-                xj = Xd[j].unsqueeze(0)
-                for g in gs:
-                    g.add_batch(xj, None)
-            mark(f"hessian subset {si} done", cur)
+                for li, g in zip(subset, gs):
+                    g.add_batch(views[linears[li][3]][j].unsqueeze(0), None)
             cur.wait_event(wev)                           # this subset's weights have landed
             for g, wd in zip(gs, wdev):
                 g.layer.weight.data = wd
         else:
-            for j in range(X.shape[0]):
-                xj = X[j].unsqueeze(0)
-                for g in gs:                              # the forward hooks of q/k/v see the same tensor
-                    g.add_batch(xj, None)
-        if os.environ.get("GPTQ_B200_DEBUG_SYNC"):
-            torch.cuda.synchronize()
-            fin = [bool(torch.isfinite(g.raw_accumulator()).all()) for g in gs]
-            print("debug: add_batch phase ok", [LINEARS[li][0] for li in subset], "S finite:", fin, file=sys.stderr)
+            for j in range(n_local):
+                for li, g in zip(subset, gs):             # the forward hooks of q/k/v see the same tensor
+                    g.add_batch(acts[linears[li][3]][j].unsqueeze(0), None)
         for g in gs:
             if world > 1:
-                gd.allreduce_hessian(g)
-                gd.fasterquant_sharded(g, **GPTQ_KW)
+                gd.allreduce_hessian(g, total_samples=NSAMPLES)
+                gd.fasterquant_sharded(g, **wl["gptq"])
             else:
-                g.fasterquant(**GPTQ_KW)
-            qw = pack_codes(g.codes, WBITS)
+                g.fasterquant(**wl["gptq"])
+            with G._prof("pack"):
+                if wl["pack"] == "linear":                # the reference's entry point: fp16 weights + [R,ng] scales / zeros
+                    ql = QuantLinear(wl["wbits"], g.columns, g.rows)
+                    ql.pack(g.layer, g.scales, g.zeros, g_idx=g.g_idx)
+                    qw = ql.qweight
+                else:
+                    qw = pack_codes(g.codes, wl["wbits"])
             if from_host:                                 # result back to the host: packed words + scales + zeros
                 outs = [qw.cpu(), g.scales.cpu(), g.zeros.cpu(), g.g_idx.cpu()]
                 d2h += sum(o.numel() * o.element_size() for o in outs)
-            results.append((qw, g.error))
+            results.append((qw, g))
             g.free()
         if from_host:                                     # activations staged, weights read: the landing area is free
             ev = torch.cuda.Event()
             ev.record(cur)
             _H2D[dev]["consumed"][si & 1] = ev
-        mark(f"fasterquant subset {si} done", cur)
     if from_host and pending is None:
         cur.wait_stream(_copy_stream(dev))
-    if trace is not None:
-        torch.cuda.synchronize()
-        t0 = trace[0][1]
-        print("e2e trace (ms since step start): " + "; ".join(f"{n} {t0.elapsed_time(e):.1f}" for n, e in trace[1:]), file=sys.stderr)
     return results, d2h, pending
 
 
+def multi_gpu_parity(wl, dev, rank, world):
+    """Outside the timed region: the FIRST linear of the layer quantized (a) sample- and row-sharded over all ranks and
+    (b) on rank 0 alone with all samples; reports how the two results compare (replicas must be bitwise equal,
+    the sharded result differs from the single-GPU one only through the summation order of the partial Hessians)."""
+    import torch.distributed as dist
+    import torch.nn as nn
+    from gptq_b200.gptq import GPTQ
+    from gptq_b200.quant import Quantizer
+    from gptq_b200 import dist as gd
+    name, R, K, a = wl["linears"][0]
+    ns = 32                                                # enough samples for a well-conditioned K x K Hessian
+    gw = torch.Generator(device=dev).manual_seed(1)
+    W = (torch.randn(R, K, device=dev, generator=gw) * 0.02).half()
+    g0 = torch.Generator(device=dev).manual_seed(100 + a)
+    chan = torch.exp(0.5 * torch.randn(K, device=dev, generator=g0))
+
+    def sample(j):
+        gj = torch.Generator(device=dev).manual_seed(1000 * (a + 1) + j)
+        return (torch.randn(1, SEQ, K, device=dev, generator=gj) * chan).half()
+
+    def run(samples, sharded):
+        lin = nn.Linear(K, R, bias=False, device="meta")
+        lin.to_empty(device=dev)
+        lin = lin.half()
+        lin.weight.data = W.clone()
+        g = GPTQ(lin)
+        g.quantizer = Quantizer()
+        g.quantizer.configure(wl["wbits"], perchannel=True, sym=False, mse=False)
+        for j in samples:
+            g.add_batch(sample(j), None)
+        with contextlib.redirect_stdout(io.StringIO()):
+            if sharded:
+                gd.allreduce_hessian(g, total_samples=ns)
+                gd.fasterquant_sharded(g, **wl["gptq"])
+            else:
+                g.fasterquant(**wl["gptq"])
+        return g.codes, lin.weight.data, g.error
+    codes_s, wq_s, err_s = run(gd.sample_shard(ns, rank, world), True)
+    # replicas: a 64-bit checksum of codes and weights, compared across ranks
+    chk = torch.stack([codes_s.long().sum(), wq_s.view(torch.int16).long().sum(),
+                       (codes_s.long() * torch.arange(1, K + 1, device=dev)).sum()])
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    replicas_equal = all(torch.equal(c, allc[0]) for c in allc)
+    out = None
+    if rank == 0:
+        codes_1, wq_1, err_1 = run(range(ns), False)
+        diff = codes_1 != codes_s
+        out = {"linear": f"{name} {R}x{K}", "samples": ns, "replicas_bitwise_equal": bool(replicas_equal),
+               "codes_equal": bool(not diff.any()), "codes_agree": float(1.0 - diff.double().mean()),
+               "rows_differing": int(diff.any(dim=1).sum()), "weights_agree": float((wq_1 == wq_s).double().mean()),
+               "error_single": err_1, "error_sharded": err_s,
+               "note": "sharded = partial Hessians summed by the all-reduce (different fp32 summation order than one GPU), rows solved "
+                       "on different ranks and gathered; gate: >= 99.9 % codes agree"}
+    dist.barrier()
+    return out
+
+
 def run_ours(args):
-    import contextlib
-    import io
     import torch.distributed as dist
     from gptq_b200 import _lib
     import gptq_b200.gptq as G
 
+    wl = WORKLOADS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -394,7 +641,7 @@ def run_ours(args):
         d2h = 0
         with contextlib.redirect_stdout(quiet):
             for _ in range(warmup):
-                quantize_layer(dev, acts, weights, world, from_host)
+                quantize_layer(wl, dev, acts, weights, world, from_host)
             carry = None
             barrier()
             G.PROFILE = [] if profile else None
@@ -404,7 +651,7 @@ def run_ours(args):
             t0 = time.perf_counter()
             e0.record()
             for i in range(steps):
-                _, d2h, carry = quantize_layer(dev, acts, weights, world, from_host, carry, prefetch_next=from_host and i + 1 < steps)
+                _, d2h, carry = quantize_layer(wl, dev, acts, weights, world, from_host, carry, prefetch_next=from_host and i + 1 < steps)
             e1.record()
             barrier()
             wall = time.perf_counter() - t0
@@ -417,14 +664,14 @@ def run_ours(args):
         return float(t.item()), wall, _lib.launch_count() - n0, prof, d2h
 
     # ---- device-resident run (value)
-    acts, weights = make_inputs(dev, rank, world, host=False)
+    acts, weights = make_inputs(wl, dev, rank, world, host=False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms, wall, launches, prof, _ = timed(acts, weights, False, args.steps, args.warmup, True)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms / args.steps
-    value = LAYER_WEIGHTS / (ms_step / 1e3) / 1e6
+    value = wl["weights"] / (ms_step / 1e3) / 1e6
 
     # per-kernel device time inside the timed region (CUDA events on the launching stream)
     agg = {}
@@ -435,26 +682,52 @@ def run_ours(args):
         d[2] += 1
     sy = agg.get("syrk", [1e-9, 0.0, 1])
     syrk_tflops = sy[1] / (sy[0] / 1e3) / 1e12
-    dense_equiv = sum(2.0 * c * c * (NSAMPLES // world) * SEQ for _, r, c, _ in LINEARS) * args.steps / (sy[0] / 1e3) / 1e12
-    roofline = {"kernel": "syrk_tc_kernel (tcgen05 Hessian accumulation)", "bound": "tensor", "achieved": syrk_tflops,
+    dense_equiv = sum(2.0 * c * c * (NSAMPLES // world) * SEQ for _, r, c, _ in wl["linears"]) * args.steps / (sy[0] / 1e3) / 1e12
+    traffic, traffic_src = syrk_traffic(prof) if world == 1 else (None, None)
+    kname = {1: "syrk_tc_kernel (tcgen05 cta_group::1, M128 x N256 per SM)"}.get(G.SYRK_VARIANT, "syrk_tc2_kernel (tcgen05 cta_group::2, M256 x N256 per CTA pair)")
+    roofline = {"kernel": kname + " -- Hessian accumulation", "bound": "tensor", "achieved": syrk_tflops,
                 "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": syrk_tflops / pk["tf_sustained"],
-                "peak_source": pk["source"] + " bf16 cuBLAS sustained", "frac_of_nominal_2250": syrk_tflops / 2250.0,
+                "peak_source": pk["source"] + " bf16 cuBLAS sustained", "frac_of_burst_peak": syrk_tflops / pk["tf_burst"],
+                "frac_of_nominal_2250": syrk_tflops / 2250.0,
                 "launches": sy[2], "avg_launch_ms": sy[0] / max(sy[2], 1), "share_of_step": sy[0] / ms,
-                "dense_equivalent_tflops": dense_equiv, "traffic": syrk_traffic(prof) if world == 1 else None,
-                "traffic_note": "DRAM read+write bytes per launch (launch-weighted over the K=4096 and K=11008 launches) from the "
-                                "committed ncu capture profiles/r01_syrk_traffic.json; algorithmic bytes per launch: 0.40 GB / 1.22 GB"}
+                "dense_equivalent_tflops": dense_equiv, "traffic": traffic,
+                "traffic_note": f"DRAM read+write bytes per launch, launch-weighted over the launch shapes of the timed region, from the "
+                                f"committed ncu capture profiles/{traffic_src}"}
     co = agg.get("colloop", [1e-9, 0.0, 1])
     hv = agg.get("hinv_upper", [1e-9, 0.0, 1])
     others = {
         "colloop": {"bound": "hbm", "achieved": co[1] / (co[0] / 1e3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "frac": co[1] / (co[0] / 1e3) / 1e9 / pk["hbm_gbs"], "share_of_step": co[0] / ms,
-                    "us_per_column": co[0] * 1e3 / (args.steps * sum(c for _, r, c, _ in LINEARS)),
+                    "us_per_column": co[0] * 1e3 / (args.steps * sum(c for _, r, c, _ in wl["linears"])),
                     "note": "sequential column recurrence: latency-bound, low HBM fraction expected (SURVEY 8d)"},
         "hinv_upper": {"bound": "fp32", "achieved": hv[1] / (hv[0] / 1e3) / 1e12, "unit": "TFLOP/s (2/3 K^3 useful)",
                        "share_of_step": hv[0] / ms},
     }
     phase_ms = {k: v[0] / args.steps for k, v in agg.items()}
-    phase_ms["unattributed (staging copies, pack, allocator, host gaps)"] = ms_step - sum(phase_ms.values())
+    phase_ms["rest (see phase_breakdown_instrumented_step)"] = ms_step - sum(phase_ms.values())
+
+    # ---- one extra, fully instrumented step (NOT part of the timed region): events around every staging copy / verify /
+    #      collective / pack, and the host time spent blocked in fasterquant's record read-back
+    G.PROFILE, G.PROFILE_FINE, G.HOST_WAIT = [], True, [0.0]
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ea.record()
+        quantize_layer(wl, dev, acts, weights, world, False)
+        eb.record()
+    torch.cuda.synchronize()
+    fine = {}
+    for name, a, b, work, _meta in G.PROFILE:
+        fine[name] = fine.get(name, 0.0) + a.elapsed_time(b)
+    fine_total = ea.elapsed_time(eb)
+    fine["unattributed"] = fine_total - sum(fine.values())
+    fine["_step_ms_with_instrumentation"] = fine_total
+    fine["_host_blocked_in_readback_ms"] = G.HOST_WAIT[0] * 1e3
+    G.PROFILE, G.PROFILE_FINE, G.HOST_WAIT = None, False, None
+
+    parity = None
+    if world > 1:
+        parity = multi_gpu_parity(wl, dev, rank, world)
     del acts, weights
     torch.cuda.empty_cache()
 
@@ -463,11 +736,11 @@ def run_ours(args):
     try:
         if args.no_e2e:
             raise RuntimeError("skipped (--no-e2e)")
-        acts_h, weights_h = make_inputs(dev, rank, world, host=True)
+        acts_h, weights_h = make_inputs(wl, dev, rank, world, host=True)
         h2d = sum(x.numel() * 2 for x in acts_h) + sum(w.numel() * 2 for w in weights_h)
         e_steps = max(1, min(args.steps, 3))
         ems, _, _, _, d2h = timed(acts_h, weights_h, True, e_steps, 1, False)
-        e2e = {"value": LAYER_WEIGHTS / (ems / e_steps / 1e3) / 1e6, "unit": "Mweights/s", "h2d_bytes_per_step": h2d * world,
+        e2e = {"value": wl["weights"] / (ems / e_steps / 1e3) / 1e6, "unit": "Mweights/s", "h2d_bytes_per_step": h2d * world,
                "d2h_bytes_per_step": d2h * world, "ms_per_step": ems / e_steps, "steps": e_steps}
         del acts_h, weights_h
     except Exception as ex:  # pinned allocation can fail on small hosts; report instead of hiding
@@ -475,20 +748,31 @@ def run_ours(args):
             import traceback
             traceback.print_exc(file=sys.stderr)
         e2e = {"value": None, "unit": "Mweights/s", "error": repr(ex)}
+    _H2D.clear()
+    torch.cuda.empty_cache()
 
     if rank == 0:
-        out = base_line(args, value, ms_step)
-        out.update({"whole_model_seconds": ms_step * N_LAYERS / 1e3, "wall_seconds_timed_region": wall,
+        out = base_line(args, wl, value, ms_step)
+        out.update({"hot_path_seconds_x_layers": ms_step * wl["n_layers"] / 1e3, "wall_seconds_timed_region": wall,
                     "hessian_tflops_issued": syrk_tflops, "hessian_tflops_dense_equivalent": dense_equiv,
-                    "roofline": roofline, "rooflines_other": others, "phase_ms_per_step": phase_ms, "clocks": clocks, "e2e": e2e,
+                    "roofline": roofline, "rooflines_other": others, "phase_ms_per_step": phase_ms,
+                    "phase_breakdown_instrumented_step": fine, "clocks": clocks, "e2e": e2e,
                     "gpu_launches": launches, "impl": "ours"})
+        if parity is not None:
+            out["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference_sample()
-            out["cpu_baseline"] = {"value": LAYER_WEIGHTS / cb["layer_seconds"] / 1e6, "unit": "Mweights/s", "cores": cb["cores"],
-                                   "kind": "port", "sample": cb["sample"], "detail": cb["measured"],
+            cb = cpu_reference_sample(wl)
+            out["cpu_baseline"] = {"value": wl["weights"] / cb["layer_seconds"] / 1e6, "unit": "Mweights/s", "cores": cb["cores"],
+                                   "kind": cb["kind"], "sample": cb["sample"], "detail": cb["measured"],
                                    "extrapolated_layer_seconds": cb["layer_seconds"]}
+        if world == 1 and not args.no_gpu_baseline:
+            try:
+                out["gpu_torch_baseline"] = reference_cuda_layer(wl, dev, 1, 1)
+            except Exception as ex:
+                out["gpu_torch_baseline"] = {"value": None, "error": repr(ex)}
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -497,18 +781,29 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
+    ap.add_argument("--config", default="llama7b", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="layer", choices=["layer", "model"])
+    ap.add_argument("--model-layers", type=int, default=0, help="--workload model: quantize only the first N decoder layers (0 = all)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "reference-cuda":
+        run_reference_cuda(args)
+        return
+    if int(os.environ.get("WORLD_SIZE", "1")) != args.gpus and args.gpus > 1:
+        # convenience: spawn torchrun ourselves when launched as plain `python bench.py --gpus N`
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.workload == "model":
+        from bench_model import run_model
+        run_model(args)
     else:
-        if int(os.environ.get("WORLD_SIZE", "1")) != args.gpus and args.gpus > 1:
-            # convenience: spawn torchrun ourselves when launched as plain `python bench.py --gpus N`
-            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
-                   "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
-            sys.exit(subprocess.call(cmd))
         run_ours(args)
 
 

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgptq_b200.so")
 
 F16, BF16, F32 = 0, 1, 2
 ABI_VERSION = 3
-SYRK_AUTO, SYRK_CTA1, SYRK_CTA2 = 0, 1, 2
+SYRK_AUTO, SYRK_CTA1, SYRK_CTA2, SYRK_CTA2_BK128 = 0, 1, 2, 3
 _DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
 
 _vp, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
@@ -29,6 +29,8 @@ SIGNATURES = {
     "gptq_b200_syrk_accum": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _f, _f, _i, _i, _vp, _sz, _vp]),
     "gptq_b200_syrk_accum_simt": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _f, _f, _vp]),
     "gptq_b200_symmetrize": (_i, [_vp, _i, _i64, _vp]),
+    "gptq_b200_tril_pack": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "gptq_b200_tril_unpack": (_i, [_vp, _i, _vp, _i64, _vp]),
     "gptq_b200_stage_input": (_i, [_vp, _i, _i64, _i, _i64, _vp, _i64, _vp]),
     "gptq_b200_compare_rows": (_i, [_vp, _i64, _vp, _i64, _i64, _i, _vp, _vp]),
     "gptq_b200_hessian_prepare": (_i, [_vp, _i, _i64, _f, _vp, _vp, _vp, _vp]),

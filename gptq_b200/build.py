@@ -69,10 +69,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if log:
                 print(log)
     if force or _stale(LIB, objs):
-        cmd = [NVCC, *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
+        tmp = LIB + ".tmp"               # link beside the target, then rename: a reader never sees a half-written library
+        cmd = [NVCC, *ARCH, "-shared", "-o", tmp, *objs, "-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 

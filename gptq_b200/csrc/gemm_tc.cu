@@ -93,7 +93,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = empty_bar + GT_STAGES;     // [2]
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -138,45 +138,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // The whole warp runs the loop and waits on the barriers; one elected lane issues.  Issued from inside
+        // `if (lane == 0)` every tcgen05 instruction was wrapped in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~35
+        // dependent instructions per MMA): with 134-cycle tf32 MMAs the single issuing thread could not keep the tensor
+        // pipe fed (ncu: 51 % active).  Warp-uniform operands stay in uniform registers.
+        {
             int stage = 0; uint32_t phase = 0;
-            int buf = 0; uint32_t bphase[2] = {0, 0};
+            int buf = 0; uint32_t bphase0 = 0, bphase1 = 0;
+            const uint32_t ring = ptx::smem_u32(smem);
+            // K-major: SWIZZLE_128B (BK = 32) or SWIZZLE_64B (BK = 16), 8-row atoms (SBO = 8 rows).  MN-major tf32:
+            // SWIZZLE_128B_BASE32B, 32-element x 4-k-row atoms: LBO = panel stride (next 32 m/n), SBO = 512.
+            constexpr uint32_t KSBO = 8 * GT_BK * 4, KLT = (GT_BK == 32) ? 2 : 4;
+            const uint32_t albo = p.a_mn ? GT_PANEL : 16, blbo = p.b_mn ? GT_PANEL : 16;
+            const uint32_t asbo = p.a_mn ? 512 : KSBO, bsbo = p.b_mn ? 512 : KSBO;
+            const uint32_t alt = p.a_mn ? 1 : KLT, blt = p.b_mn ? 1 : KLT;
+            const uint64_t a_hi64 = ptx::make_smem_desc(0, albo, asbo, alt), b_hi64 = ptx::make_smem_desc(0, blbo, bsbo, blt);
+            // K-major: +32 B per k-step inside the swizzle row; MN-major: +1024 B (8 k-rows)   (in 16-byte units)
+            const uint32_t astep = p.a_mn ? (1024 >> 4) : (32 >> 4), bstep = p.b_mn ? (1024 >> 4) : (32 >> 4);
             for (int kb = 0; kb < nkb; ++kb) {
                 const bool chunk_start = (kb % GT_CHUNK) == 0;
                 if (chunk_start) {
-                    ptx::mbar_wait(&tempty_bar[buf], bphase[buf] ^ 1);
+                    ptx::mbar_wait(&tempty_bar[buf], (buf ? bphase1 : bphase0) ^ 1);
                     ptx::tc_fence_after();
                 }
                 ptx::mbar_wait(&conv_bar[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t sA = ptx::smem_u32(smem + stage * GT_STAGE_BYTES);
-                const uint32_t sB = sA + 2 * GT_A_BYTES;
+                const uint32_t sA = (ring + stage * GT_STAGE_BYTES) >> 4;
+                const uint32_t sB = sA + ((2 * GT_A_BYTES) >> 4);
                 const uint32_t d_tmem = tmem_base + buf * GT_BN;
 #pragma unroll
                 for (int ks = 0; ks < GT_BK / 8; ++ks) {
-                    // K-major: +32 B per k-step inside the swizzle row; MN-major: +1024 B (8 k-rows)
-                    const uint32_t aoff = p.a_mn ? ks * 1024 : ks * 32;
-                    const uint32_t boff = p.b_mn ? ks * 1024 : ks * 32;
-                    // K-major: SWIZZLE_128B (BK = 32) or SWIZZLE_64B (BK = 16), 8-row atoms (SBO = 8 rows).  MN-major tf32:
-                    // SWIZZLE_128B_BASE32B, 32-element x 4-k-row atoms: LBO = panel stride (next 32 m/n), SBO = 512.
-                    constexpr uint32_t KSBO = 8 * GT_BK * 4, KLT = (GT_BK == 32) ? 2 : 4;
-                    const uint32_t albo = p.a_mn ? GT_PANEL : 16, blbo = p.b_mn ? GT_PANEL : 16;
-                    const uint32_t asbo = p.a_mn ? 512 : KSBO, bsbo = p.b_mn ? 512 : KSBO;
-                    const uint32_t alt = p.a_mn ? 1 : KLT, blt = p.b_mn ? 1 : KLT;
-                    const uint64_t ahi = ptx::make_smem_desc(sA + aoff, albo, asbo, alt);
-                    const uint64_t alo = ptx::make_smem_desc(sA + GT_A_BYTES + aoff, albo, asbo, alt);
-                    const uint64_t bhi = ptx::make_smem_desc(sB + boff, blbo, bsbo, blt);
-                    const uint64_t blo = ptx::make_smem_desc(sB + GT_B_BYTES + boff, blbo, bsbo, blt);
+                    const uint64_t ahi = a_hi64 | (uint64_t)(sA + ks * astep);
+                    const uint64_t alo = a_hi64 | (uint64_t)(sA + (GT_A_BYTES >> 4) + ks * astep);
+                    const uint64_t bhi = b_hi64 | (uint64_t)(sB + ks * bstep);
+                    const uint64_t blo = b_hi64 | (uint64_t)(sB + (GT_B_BYTES >> 4) + ks * bstep);
                     const uint32_t acc0 = (chunk_start && ks == 0) ? 0u : 1u;
-                    ptx::mma_tf32_ss(d_tmem, alo, bhi, p.idesc, acc0);        // small terms first
-                    ptx::mma_tf32_ss(d_tmem, ahi, blo, p.idesc, 1u);
-                    ptx::mma_tf32_ss(d_tmem, ahi, bhi, p.idesc, 1u);
+                    ptx::mma_tf32_ss_elect(d_tmem, alo, bhi, p.idesc, acc0);        // small terms first
+                    ptx::mma_tf32_ss_elect(d_tmem, ahi, blo, p.idesc, 1u);
+                    ptx::mma_tf32_ss_elect(d_tmem, ahi, bhi, p.idesc, 1u);
                 }
-                ptx::tc_commit(&empty_bar[stage]);
+                ptx::tc_commit_elect(&empty_bar[stage]);
                 if (++stage == GT_STAGES) { stage = 0; phase ^= 1; }
                 if ((kb % GT_CHUNK) == GT_CHUNK - 1 || kb == nkb - 1) {
-                    ptx::tc_commit(&tfull_bar[buf]);
-                    bphase[buf] ^= 1;
+                    ptx::tc_commit_elect(&tfull_bar[buf]);
+                    if (buf) bphase1 ^= 1; else bphase0 ^= 1;
                     buf ^= 1;
                 }
             }

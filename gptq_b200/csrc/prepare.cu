@@ -136,6 +136,20 @@ __global__ void symmetrize_kernel(float* __restrict__ H, int K, int64_t ldh) {
     }
 }
 
+// ------------------------------------------------------------------ lower triangle <-> packed rows (multi-GPU exchange #1)
+// packed[r (r + 1) / 2 + c] = S[r][c] for c <= r: what the all-reduce of the partial Hessians has to carry (SURVEY 5 / 8e:
+// the lower triangle suffices, half the bytes of the K x K square).  One CTA per row, grid-stride; coalesced on both sides.
+__global__ void __launch_bounds__(256)
+tril_pack_kernel(const float* __restrict__ S, int K, int64_t lds, float* __restrict__ packed, int unpack) {
+    for (int r = blockIdx.x; r < K; r += gridDim.x) {
+        const int64_t off = (int64_t)r * (r + 1) / 2;
+        float* p = packed + off;
+        float* row = const_cast<float*>(S) + (int64_t)r * lds;
+        if (unpack) { for (int c = threadIdx.x; c <= r; c += blockDim.x) row[c] = p[c]; }
+        else        { for (int c = threadIdx.x; c <= r; c += blockDim.x) p[c] = row[c]; }
+    }
+}
+
 // ------------------------------------------------------------------ staging copy
 template <typename T>
 __global__ void stage_kernel(const T* __restrict__ src, int64_t tokens, int K, int64_t lds, T* __restrict__ dst, int64_t ldd) {
@@ -320,6 +334,22 @@ extern "C" int gptq_b200_symmetrize(float* H, int K, int64_t ldh, void* stream) 
     if (K == 0) return 0;
     int nb = cdiv(K, 32);
     symmetrize_kernel<<<dim3(nb, nb), dim3(32, 8), 0, as_stream(stream)>>>(H, K, ldh);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_tril_pack(const float* S, int K, int64_t lds, float* packed, void* stream) {
+    GQ_ARG(S, 1, "null"); GQ_ARG(K >= 0, 2, "K<0"); GQ_ARG(lds >= K, 3, "lds<K"); GQ_ARG(packed, 4, "null");
+    if (K == 0) return 0;
+    tril_pack_kernel<<<K < 4 * num_sms() ? K : 4 * num_sms(), 256, 0, as_stream(stream)>>>(S, K, lds, packed, 0);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_tril_unpack(const float* packed, int K, float* S, int64_t lds, void* stream) {
+    GQ_ARG(packed, 1, "null"); GQ_ARG(K >= 0, 2, "K<0"); GQ_ARG(S, 3, "null"); GQ_ARG(lds >= K, 4, "lds<K");
+    if (K == 0) return 0;
+    tril_pack_kernel<<<K < 4 * num_sms() ? K : 4 * num_sms(), 256, 0, as_stream(stream)>>>(S, K, lds, const_cast<float*>(packed), 1);
     GQ_LAUNCHED();
     return 0;
 }

@@ -348,8 +348,8 @@ static SyrkPlan make_plan(int K, int64_t T) {
 
 // syrk_tc2.cu: the CTA-pair (cta_group::2) kernel
 size_t syrk2_workspace_bytes(int K, int64_t tokens);
-int syrk2_launch(const CUtensorMap& tmap, int dtype, int64_t tokens, int K, float* H, int64_t ldh, float alpha, float beta,
-                 int chunk, void* ws, size_t ws_bytes, cudaStream_t st);
+int syrk2_launch(const CUtensorMap& tmap, int bk, int dtype, int64_t tokens, int K, float* H, int64_t ldh, float alpha, float beta,
+                 int chunk, int sw, int sh, void* ws, size_t ws_bytes, cudaStream_t st);
 
 static size_t syrk1_workspace_bytes(int K, int64_t tokens) {
     if (K <= 0 || tokens <= 0) return 0;
@@ -363,6 +363,7 @@ static size_t syrk1_workspace_bytes(int K, int64_t tokens) {
 using namespace gq;
 
 extern "C" size_t gptq_b200_syrk_workspace_bytes(int K, int64_t tokens, int variant) {
+    variant &= 0xFF;
     return variant == GPTQ_B200_SYRK_CTA1 ? syrk1_workspace_bytes(K, tokens) : syrk2_workspace_bytes(K, tokens);
 }
 
@@ -374,7 +375,12 @@ extern "C" int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, in
     GQ_ARG(ldx >= K && ldx % 8 == 0, 5, "ldx must be >= K and a multiple of 8 (TMA 16-byte stride)");
     GQ_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, 1, "X must be 16-byte aligned");
     GQ_ARG(H, 6, "null"); GQ_ARG(ldh >= K, 7, "ldh<K"); GQ_ARG(chunk_tokens >= 0, 10, "chunk_tokens<0");
-    GQ_ARG(variant >= GPTQ_B200_SYRK_AUTO && variant <= GPTQ_B200_SYRK_CTA2, 11, "variant must be 0 (auto), 1 (cta_group::1) or 2 (cta_group::2)");
+    // tuning bits above the kernel selector (perf experiments; 0 = defaults): tile-order chunk sw (bits 8-15) x sh (bits 16-23),
+    // bit 24 = TMA L2 promotion 256 B instead of the pair kernel's 128 B (which read 10 % less DRAM at K = 11008)
+    const int tune_sw = (variant >> 8) & 0xFF, tune_sh = (variant >> 16) & 0xFF;
+    const int tune_p128 = ((variant & 0xFF) == GPTQ_B200_SYRK_CTA1) ? 0 : !((variant >> 24) & 1);
+    variant &= 0xFF;
+    GQ_ARG(variant >= GPTQ_B200_SYRK_AUTO && variant <= GPTQ_B200_SYRK_CTA2_BK128, 11, "variant must be one of GPTQ_B200_SYRK_*");
     if (tokens == 0) return 0;                 // beta handling for empty input is the caller's business
     cudaStream_t st = as_stream(stream);
     const bool pair = variant != GPTQ_B200_SYRK_CTA1;
@@ -387,15 +393,16 @@ extern "C" int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, in
     CUtensorMap tmap;
     cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)tokens};
     cuuint64_t gstr[1] = {(cuuint64_t)ldx * 2};
-    cuuint32_t box[2] = {64, SY_BK};
+    const int pair_bk = (variant == GPTQ_B200_SYRK_CTA2) ? 64 : 128;
+    cuuint32_t box[2] = {64, (cuuint32_t)(pair ? pair_bk : SY_BK)};
     cuuint32_t estr[2] = {1, 1};
     CUresult cr = enc(&tmap, dtype == GPTQ_B200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
                       const_cast<void*>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                      tune_p128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return set_err(1000 + (int)cr, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
     int chunk = chunk_tokens > 0 ? chunk_tokens : 512;
-    if (pair) return syrk2_launch(tmap, dtype, tokens, K, H, ldh, alpha, beta, chunk, ws, ws_bytes, st);
+    if (pair) return syrk2_launch(tmap, pair_bk, dtype, tokens, K, H, ldh, alpha, beta, chunk, tune_sw, tune_sh, ws, ws_bytes, st);
 
     GQ_ONCE_PER_DEVICE(GQ_CUDA(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM)));
     SyrkParams p;
@@ -406,7 +413,7 @@ extern "C" int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, in
     p.H = H; p.ldh = ldh; p.alpha = alpha; p.beta = beta;
     p.partial = static_cast<float*>(ws);
     p.idesc = ptx::make_idesc(dtype == GPTQ_B200_F16 ? 0 : 1, 1, 1, SY_BM, SY_BN);
-    p.sw = 12; p.sh = 12;          // 144 tiles ~ one wave (6 x 24 and 16 x 9 measured 1-2 % slower)
+    p.sw = tune_sw ? tune_sw : 12; p.sh = tune_sh ? tune_sh : 12;          // 144 tiles ~ one wave (6 x 24 and 16 x 9 measured 1-2 % slower)
     const int n_items = pl.n_tiles * pl.splits;
     const int grid = n_items < num_sms() ? n_items : num_sms();
     syrk_tc_kernel<<<grid, SY_THREADS, SY_SMEM, st>>>(tmap, p);

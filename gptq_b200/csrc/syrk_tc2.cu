@@ -32,18 +32,22 @@
 namespace gq {
 
 constexpr int S2_T = 256;                        // tile edge: MMA M across the pair = MMA N
-constexpr int S2_BK = 64;                        // tokens per pipeline stage
-constexpr int S2_STAGES = 6;
-constexpr int S2_PANEL = 64 * 128;               // bytes: 64 tokens x 64 channels x 2 B
-constexpr int S2_OP_BYTES = 2 * S2_PANEL;        // one operand half of one CTA: 128 channels x 64 tokens
-constexpr int S2_STAGE_BYTES = 2 * S2_OP_BYTES;  // A half + B half
 constexpr int S2_THREADS = 320;                  // TMA warp, MMA warp, 8 epilogue warps
-constexpr int S2_SMEM = S2_STAGES * S2_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int S2_RING_BYTES = 6 * 32768;         // operand ring per CTA: BK x STAGES = 384 tokens in flight
+constexpr int S2_SMEM = S2_RING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// BK = tokens per pipeline stage (one full/empty barrier round trip and one tcgen05.commit per BK / 16 MMAs):
+//   <64, 6>: 32 KB stages;  <128, 3>: 64 KB stages, half the barrier traffic of the single issuing thread.
+template <int BK, int STAGES> struct S2Cfg {
+    static constexpr int PANEL = BK * 128;              // bytes: BK tokens x 64 channels x 2 B (TMA box {64, BK})
+    static constexpr int OP_BYTES = 2 * PANEL;          // one operand half of one CTA: 128 channels x BK tokens
+    static constexpr int STAGE_BYTES = 2 * OP_BYTES;    // A half + B half
+    static_assert(STAGES * STAGE_BYTES <= S2_RING_BYTES, "ring too large");
+};
 
 struct Syrk2Params {
     int K; int64_t T; int nb; int n_tiles; int splits;
-    int64_t tokens_per_split;   // multiple of S2_BK
-    int chunk;                  // multiple of S2_BK
+    int64_t tokens_per_split;   // multiple of BK
+    int chunk;                  // multiple of BK
     float* H; int64_t ldh; float alpha; float beta;
     float* partial;             // [splits][n_tiles][256][256] when splits > 1
     uint32_t idesc;
@@ -69,8 +73,12 @@ __device__ __forceinline__ void decode_tile2(int t, int nb, int sw, int sh, int&
     bi = nb - 1; bj = 0;          // unreachable for t < n_tiles
 }
 
+template <int S2_BK, int S2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
+    constexpr int S2_PANEL = S2Cfg<S2_BK, S2_STAGES>::PANEL;
+    constexpr int S2_OP_BYTES = S2Cfg<S2_BK, S2_STAGES>::OP_BYTES;
+    constexpr int S2_STAGE_BYTES = S2Cfg<S2_BK, S2_STAGES>::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S2_STAGES * S2_STAGE_BYTES);   // used in the leader only
@@ -79,7 +87,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
     uint64_t* tempty_bar = tfull_bar + 2;            // [2] used in the leader only: 8 epilogue warps x 2 CTAs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = ptx::warp_idx_uniform(), lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
@@ -131,38 +139,43 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer (leader CTA only)
-        if (rank == 0 && lane == 0) {
+        // The whole warp runs the loop and waits on the barriers; one elected lane issues (see ptx::mma_f16_ss2_elect).
+        if (rank == 0) {
+            // descriptor = constant high part | (shared address >> 4): SWIZZLE_128B, LBO = panel, SBO = 1024, version 1
+            constexpr uint64_t DESC_HI = ((uint64_t)((S2_PANEL >> 4) & 0x3FFF) << 16) | ((uint64_t)((1024 >> 4) & 0x3FFF) << 32) |
+                                         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+            const uint32_t ring_lo = ptx::smem_u32(smem) >> 4;
             int stage = 0; uint32_t phase = 0;
-            int buf = 0; uint32_t bphase[2] = {0, 0};
+            int buf = 0; uint32_t bphase0 = 0, bphase1 = 0;
             for (int item = cid; item < n_items; item += ncl) {
                 const int tile = item / p.splits, split = item - tile * p.splits;
                 int bi, bj; decode_tile2(tile, p.nb, p.sw, p.sh, bi, bj);
-                const int a_off = (bi == bj) ? S2_OP_BYTES : 0;       // diagonal: A is this CTA's B half
+                const uint32_t a_off_lo = (bi == bj) ? (S2_OP_BYTES >> 4) : 0;       // diagonal: A is this CTA's B half
                 const int64_t t0 = (int64_t)split * p.tokens_per_split;
                 const int64_t t1 = min(t0 + p.tokens_per_split, p.T);
                 for (int64_t c0 = t0; c0 < t1; c0 += p.chunk) {
-                    const int64_t c1 = min(c0 + (int64_t)p.chunk, t1);
-                    ptx::mbar_wait(&tempty_bar[buf], bphase[buf] ^ 1);   // both epilogues have drained this buffer
+                    const int nst = (int)((min(c0 + (int64_t)p.chunk, t1) - c0 + S2_BK - 1) / S2_BK);
+                    ptx::mbar_wait(&tempty_bar[buf], (buf ? bphase1 : bphase0) ^ 1);   // both epilogues have drained this buffer
                     ptx::tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * S2_T;
                     uint32_t acc = 0;
-                    for (int64_t t = c0; t < c1; t += S2_BK) {
+                    for (int s_ = 0; s_ < nst; ++s_) {
                         ptx::mbar_wait(&full_bar[stage], phase);
                         ptx::tc_fence_after();
-                        const uint32_t sbase = ptx::smem_u32(smem + stage * S2_STAGE_BYTES);
+                        const uint32_t st_lo = ring_lo + stage * (S2_STAGE_BYTES >> 4);
 #pragma unroll
                         for (int ks = 0; ks < S2_BK / 16; ++ks) {
-                            // 16 tokens = 2 K-atoms of 8 rows x 128 B; 128 channels per CTA = 2 MN atoms (LBO = panel)
-                            const uint64_t ad = ptx::make_smem_desc_sw128(sbase + a_off + ks * 2048, S2_PANEL, 1024);
-                            const uint64_t bd = ptx::make_smem_desc_sw128(sbase + S2_OP_BYTES + ks * 2048, S2_PANEL, 1024);
-                            ptx::mma_f16_ss2(d_tmem, ad, bd, p.idesc, acc);
+                            // 16 tokens = 2 K-atoms of 8 rows x 128 B = 2048 B; 128 channels per CTA = 2 MN atoms (LBO = panel)
+                            const uint64_t ad = DESC_HI | (uint64_t)(st_lo + a_off_lo + ks * (2048 >> 4));
+                            const uint64_t bd = DESC_HI | (uint64_t)(st_lo + (S2_OP_BYTES >> 4) + ks * (2048 >> 4));
+                            ptx::mma_f16_ss2_elect(d_tmem, ad, bd, p.idesc, acc);
                             acc = 1;
                         }
-                        ptx::tc_commit2_mc(&empty_bar[stage], 3);       // stage reusable in both CTAs once these MMAs retire
+                        ptx::tc_commit2_mc_elect(&empty_bar[stage], 3);   // stage reusable in both CTAs once these MMAs retire
                         if (++stage == S2_STAGES) { stage = 0; phase ^= 1; }
                     }
-                    ptx::tc_commit2_mc(&tfull_bar[buf], 3);             // chunk complete -> both epilogues
-                    bphase[buf] ^= 1;
+                    ptx::tc_commit2_mc_elect(&tfull_bar[buf], 3);         // chunk complete -> both epilogues
+                    if (buf) bphase1 ^= 1; else bphase0 ^= 1;
                     buf ^= 1;
                 }
             }
@@ -279,6 +292,8 @@ syrk2_reduce_kernel(const float* __restrict__ partial, int n_tiles, int splits, 
 struct Syrk2Plan { int nb, n_tiles, splits, clusters; int64_t tokens_per_split; };
 
 // Clusters of two 197 KB CTAs that can be resident at once (one per TPC: 74 on a B200), cached per device.
+constexpr int S2_PLAN_BK = 128;       // splits / chunks are planned in units valid for both stage depths
+
 static int max_clusters() {
     static std::atomic<int> cache[256] = {};
     const int dev = cur_device();
@@ -292,7 +307,7 @@ static int max_clusters() {
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, syrk_tc2_kernel, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / 2; }
+        if (cudaOccupancyMaxActiveClusters(&n, syrk_tc2_kernel<64, 6>, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = num_sms() / 2; }
         if (n > num_sms() / 2) n = num_sms() / 2;
         v = n;
         cache[slot].store(v, std::memory_order_relaxed);
@@ -305,16 +320,16 @@ static Syrk2Plan make_plan2(int K, int64_t T, int clusters) {
     pl.clusters = clusters;
     pl.nb = cdiv(K, S2_T);
     pl.n_tiles = pl.nb * (pl.nb + 1) / 2;
-    const int64_t kblocks = (T + S2_BK - 1) / S2_BK;
+    const int64_t kblocks = (T + S2_PLAN_BK - 1) / S2_PLAN_BK;
     int splits = 1;
     if (pl.n_tiles < clusters) {
         splits = clusters / pl.n_tiles;
-        const int64_t max_splits = (kblocks + 7) / 8;            // at least 8 k-blocks (512 tokens) per split
+        const int64_t max_splits = (kblocks + 3) / 4;            // at least 4 k-blocks (512 tokens) per split
         if (splits > max_splits) splits = (int)max_splits;
         if (splits < 1) splits = 1;
     }
     const int64_t kb_per = (kblocks + splits - 1) / splits;
-    pl.tokens_per_split = kb_per * S2_BK;
+    pl.tokens_per_split = kb_per * S2_PLAN_BK;
     pl.splits = (int)((kblocks + kb_per - 1) / kb_per);
     if (pl.splits < 1) pl.splits = 1;
     return pl;
@@ -328,23 +343,29 @@ size_t syrk2_workspace_bytes(int K, int64_t tokens) {
     return (size_t)pl.splits * pl.n_tiles * S2_T * S2_T * sizeof(float);
 }
 
-int syrk2_launch(const CUtensorMap& tmap, int dtype, int64_t tokens, int K, float* H, int64_t ldh, float alpha, float beta,
-                 int chunk, void* ws, size_t ws_bytes, cudaStream_t st) {
-    GQ_ONCE_PER_DEVICE(GQ_CUDA(cudaFuncSetAttribute(syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM)));
+int syrk2_launch(const CUtensorMap& tmap, int bk, int dtype, int64_t tokens, int K, float* H, int64_t ldh, float alpha, float beta,
+                 int chunk, int sw, int sh, void* ws, size_t ws_bytes, cudaStream_t st) {
+    GQ_ONCE_PER_DEVICE({
+        GQ_CUDA(cudaFuncSetAttribute(syrk_tc2_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+        GQ_CUDA(cudaFuncSetAttribute(syrk_tc2_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
+    });
     const Syrk2Plan pl = make_plan2(K, tokens, max_clusters());
     const size_t need = pl.splits > 1 ? (size_t)pl.splits * pl.n_tiles * S2_T * S2_T * sizeof(float) : 0;
     if (need && (!ws || ws_bytes < need)) return set_err(-12, "syrk_accum: workspace too small (%zu < %zu)", ws_bytes, need);
     Syrk2Params p;
     p.K = K; p.T = tokens; p.nb = pl.nb; p.n_tiles = pl.n_tiles; p.splits = pl.splits;
     p.tokens_per_split = pl.tokens_per_split;
-    p.chunk = ((chunk + S2_BK - 1) / S2_BK) * S2_BK;
+    p.chunk = ((chunk + S2_PLAN_BK - 1) / S2_PLAN_BK) * S2_PLAN_BK;
     p.H = H; p.ldh = ldh; p.alpha = alpha; p.beta = beta;
     p.partial = static_cast<float*>(ws);
     p.idesc = ptx::make_idesc(dtype == GPTQ_B200_F16 ? 0 : 1, 1, 1, S2_T, S2_T);
-    p.sw = 8; p.sh = 9;                       // 72 tiles ~ one wave of 74 clusters: (8 + 9) x 256 = 4352 channels per wave
+    // 72 tiles ~ one wave of 74 clusters.  ncu at K = 11008 (721 MB slab, profiles/r02_syrk_tile_order_sweep.md): 12 x 6 reads
+    // 5.0 GB from DRAM, 8 x 9 5.6 GB, 6 x 12 5.2 GB, 4 x 18 5.9 GB, 43 x 2 8.0 GB; durations within 2 % of each other
+    p.sw = sw ? sw : 12; p.sh = sh ? sh : 6;
     const int n_items = pl.n_tiles * pl.splits;
     const int grid = 2 * (n_items < pl.clusters ? n_items : pl.clusters);
-    syrk_tc2_kernel<<<grid, S2_THREADS, S2_SMEM, st>>>(tmap, p);
+    if (bk == 128) syrk_tc2_kernel<128, 3><<<grid, S2_THREADS, S2_SMEM, st>>>(tmap, p);
+    else syrk_tc2_kernel<64, 6><<<grid, S2_THREADS, S2_SMEM, st>>>(tmap, p);
     GQ_LAUNCHED();
     if (pl.splits > 1) {
         syrk2_reduce_kernel<<<pl.n_tiles, 256, 0, st>>>(p.partial, pl.n_tiles, pl.splits, pl.nb, K, H, ldh, alpha, beta, p.sw, p.sh);

@@ -88,21 +88,24 @@ def _side_stream(dev):
 # Optional per-call device timing: set ``gptq_b200.gptq.PROFILE = []`` and every C-ABI hot call appends
 # (name, start_event, end_event, work) recorded on the launching stream (bench.py reads it after a sync).
 PROFILE = None
+PROFILE_FINE = False      # also time every staging copy / verification (hundreds of event pairs per layer: diagnostic runs only)
+HOST_WAIT = None          # [seconds] accumulated host time blocked in fasterquant's record read-back, when set to a list
 
 
 class _prof:
-    def __init__(self, name, work=0.0, meta=None):
+    def __init__(self, name, work=0.0, meta=None, fine=False):
         self.name, self.work, self.meta = name, work, meta
+        self.on = PROFILE is not None and (PROFILE_FINE or not fine)
 
     def __enter__(self):
-        if PROFILE is not None:
+        if self.on:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)
             self.a.record()
         return self
 
     def __exit__(self, *exc):
-        if PROFILE is not None:
+        if self.on:
             self.b.record()
             PROFILE.append((self.name, self.a, self.b, self.work, self.meta))
         return False
@@ -236,9 +239,10 @@ class _Accumulator:
         if in_slab:                                        # the common case: no slicing, plain pointer arithmetic
             st_ = self.stage
             ld = st_.stride(0)
-            rc = 0 if tokens == 0 else lib.gptq_b200_stage_input(
-                x.data_ptr(), _lib.dt(x), tokens, K, x.stride(0), st_.data_ptr() + self.staged * ld * st_.element_size(), ld,
-                torch.cuda.current_stream().cuda_stream)
+            with _prof("staging", fine=True):
+                rc = 0 if tokens == 0 else lib.gptq_b200_stage_input(
+                    x.data_ptr(), _lib.dt(x), tokens, K, x.stride(0), st_.data_ptr() + self.staged * ld * st_.element_size(), ld,
+                    torch.cuda.current_stream().cuda_stream)
             if rc:
                 _lib.check(rc, "stage_input")
             self.last = (self.staged, tokens, self.count)  # resolved lazily by GPTQ.input
@@ -276,8 +280,9 @@ class _Accumulator:
         self.verified += 1
         if SHARE_VERIFY != "full" and self.verified > VERIFY_FULL_BATCHES * max(self.members - 1, 1) and rows >= VERIFY_ROW_STRIDE:
             rows, ldx, ld = rows // VERIFY_ROW_STRIDE, ldx * VERIFY_ROW_STRIDE, ld * VERIFY_ROW_STRIDE
-        rc = _lib.load().gptq_b200_compare_rows(x.data_ptr(), ldx, ref_ptr, ld, rows, self.K,
-                                                self.flag.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        with _prof("verify", fine=True):
+            rc = _lib.load().gptq_b200_compare_rows(x.data_ptr(), ldx, ref_ptr, ld, rows, self.K,
+                                                    self.flag.data_ptr(), torch.cuda.current_stream().cuda_stream)
         if rc:
             _lib.check(rc, "compare_rows")
 
@@ -372,11 +377,12 @@ class _Accumulator:
         self.wait_syrk()
         self._unregister()
         H = self.S
-        _lib.check(lib.gptq_b200_symmetrize(H.data_ptr(), K, K, _lib.stream()), "symmetrize")
-        if n > 0:
-            H.mul_(2.0 / n)
-        self.dead = torch.empty(K, device=self.dev, dtype=torch.uint8)
-        _lib.check(lib.gptq_b200_dead_columns(H.data_ptr(), K, K, self.dead.data_ptr(), _lib.stream()), "dead_columns")
+        with _prof("prologue"):
+            _lib.check(lib.gptq_b200_symmetrize(H.data_ptr(), K, K, _lib.stream()), "symmetrize")
+            if n > 0:
+                H.mul_(2.0 / n)
+            self.dead = torch.empty(K, device=self.dev, dtype=torch.uint8)
+            _lib.check(lib.gptq_b200_dead_columns(H.data_ptr(), K, K, self.dead.data_ptr(), _lib.stream()), "dead_columns")
         self.H, self.S, self.n_final, self.sealed = H, None, n, True
         if self.last is not None:      # gptq.py:63 keeps self.input after fasterquant: reduce it before the slab goes away
             self.input_mean = _last_input(self)
@@ -571,6 +577,7 @@ class GPTQ:
         self._H = None                 # materialised (2/n)*S, full symmetric, or a user-provided H
         self._consumed = False
         self._input = None             # gptq.py:63 self.input, kept after the accumulator is released
+        self._error = self._error_dev = None
 
     # ------------------------------------------------------------------ Hessian (gptq.py:38-65)
     @_on_device
@@ -699,6 +706,22 @@ class GPTQ:
     @H.deleter
     def H(self):
         self._H = None
+
+    @property
+    def error(self):
+        """sum(Losses) of the last fasterquant (gptq.py:294 prints it).  After dist.fasterquant_sharded it is the sum over
+        all row shards, kept on the device and read (one sync) only when asked for."""
+        if self._error is None and self._error_dev is not None:
+            self._error = float(self._error_dev.item())
+        return self._error
+
+    @error.setter
+    def error(self, value):
+        self._error = value
+
+    def error_tensor(self):
+        """The same value as a float64 device tensor of one element (no host sync)."""
+        return self._error_dev
 
     @property
     def input(self):
@@ -844,8 +867,11 @@ class GPTQ:
         # (info, sharing flag, loss) is read back with a single copy.  gptq.py:292 calls torch.cuda.synchronize();
         # everything here was issued on the current stream, so the stream-ordered blocking copy is the synchronisation --
         # a device-wide sync would also wait for unrelated streams (e.g. the caller's H2D prefetch).
+        t_wait = time.perf_counter() if HOST_WAIT is not None else 0.0
         rec = torch.cat([info.to(torch.float64), (flag if flag is not None else info.new_zeros(1)).to(torch.float64),
                          out["loss"]]).cpu()
+        if HOST_WAIT is not None:
+            HOST_WAIT[0] += time.perf_counter() - t_wait
         self._release()
         if rec[1] != 0:
             raise RuntimeError("GPTQ: a batch assumed identical for linears sharing one Hessian accumulator differed "
@@ -856,7 +882,7 @@ class GPTQ:
             raise torch.linalg.LinAlgError(
                 f"linalg.cholesky: The factorization could not be completed because the input is not positive-definite "
                 f"(the leading minor of order {bad} is not positive-definite).")
-        self.error = float(rec[2])
+        self._error, self._error_dev = float(rec[2]), out["loss"]
         print('time %.2f' % (time.time() - tick))
         print('error', self.error)
 

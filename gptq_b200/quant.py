@@ -191,18 +191,41 @@ def _compute_device(t: torch.Tensor) -> torch.device:
 class QuantLinear(nn.Module):
     """Packed linear layer; ``bits`` in {2,3,4,8}.  ``Quant3Linear`` is the reference's class (bits=3)."""
 
-    def __init__(self, bits, infeatures, outfeatures, faster=False):
+    def __init__(self, bits, infeatures, outfeatures, faster=False, groupsize=-1):
         super().__init__()
         if infeatures % 32:
             raise ValueError("infeatures must be a multiple of 32")
         self.bits = bits
         self.infeatures = infeatures
         self.outfeatures = outfeatures
-        self.register_buffer("zeros", torch.zeros((outfeatures, 1)))
-        self.register_buffer("scales", torch.zeros((outfeatures, 1)))
+        self.groupsize = groupsize
+        ng = 1 if groupsize in (-1, None) else (infeatures + groupsize - 1) // groupsize
+        # the reference's buffers (quant.py:144-149: zeros / scales [R,1], bias [R], qweight [K/32*bits, R]); with groups the
+        # scale tables are [R, ngroups] and g_idx [K] maps every input channel to its group (act-order + static groups)
+        self.register_buffer("zeros", torch.zeros((outfeatures, ng)))
+        self.register_buffer("scales", torch.zeros((outfeatures, ng)))
         self.register_buffer("bias", torch.zeros(outfeatures))
         self.register_buffer("qweight", torch.zeros((infeatures // 32 * bits, outfeatures), dtype=torch.int))
+        self.register_buffer("g_idx", torch.zeros(infeatures, dtype=torch.int32))
         self.faster = faster
+
+    # ---- checkpoint format (opt.py:362-402: torch.save(model.state_dict()) / load_state_dict on a make_quant'ed model).
+    # Per-row layers are saved with exactly the reference's four keys (no g_idx), so reference checkpoints load here and
+    # per-row checkpoints written here load in the reference; grouped layers add their [R,ngroups] tables and g_idx.
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        super()._save_to_state_dict(destination, prefix, keep_vars)
+        if self.scales.dim() < 2 or self.scales.shape[1] == 1:
+            destination.pop(prefix + "g_idx", None)
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        for name in ("scales", "zeros"):
+            t = state_dict.get(prefix + name)
+            if t is not None and t.dim() == 2 and t.shape[0] == self.outfeatures and t.shape != getattr(self, name).shape:
+                setattr(self, name, torch.zeros(t.shape, dtype=getattr(self, name).dtype, device=getattr(self, name).device))
+        if prefix + "g_idx" not in state_dict:          # per-row checkpoint (the reference's format)
+            state_dict = dict(state_dict)
+            state_dict[prefix + "g_idx"] = torch.zeros(self.infeatures, dtype=torch.int32)
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
     def pack(self, linear, scales, zeros, g_idx=None):
         """quant.py:152-187.  ``scales``/``zeros`` are [R,1] like the reference, or [R,ngroups] with ``g_idx`` [K]."""
@@ -227,8 +250,7 @@ class QuantLinear(nn.Module):
             if g_idx is None:
                 raise ValueError("grouped scales need g_idx")
             gi = g_idx.to(device=dev, dtype=torch.int32).contiguous()
-        if gi is not None:
-            self.g_idx = gi.to(orig)
+        self.g_idx = gi.to(orig) if gi is not None else torch.zeros(K, dtype=torch.int32, device=orig)
         qweight = torch.empty((K * self.bits // 32, R), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             _lib.check(_lib.load().gptq_b200_pack_weights(W.data_ptr(), _lib.dt(W), R, K, W.stride(0), s2.data_ptr(),
@@ -252,10 +274,7 @@ class QuantLinear(nn.Module):
             s2 = self.scales.to(dev).float().reshape(self.outfeatures, -1).contiguous()
             z2 = self.zeros.to(dev).float().reshape(self.outfeatures, -1).contiguous()
             ng = s2.shape[1]
-            gi = getattr(self, "g_idx", None)
-            gi = None if gi is None else gi.to(device=dev, dtype=torch.int32).contiguous()
-            if ng > 1 and gi is None:
-                raise ValueError("grouped scales need g_idx")
+            gi = self.g_idx.to(device=dev, dtype=torch.int32).contiguous() if ng > 1 else None
             _lib.check(_lib.load().gptq_b200_vecquant_matvec(xv.data_ptr(), _lib.dt(xv), qw.data_ptr(), self.outfeatures,
                                                              self.infeatures, self.bits, s2.data_ptr(), z2.data_ptr(), ng,
                                                              _lib.ptr(gi), 0, y.data_ptr(), _lib.stream()), "vecquant_matvec")
@@ -264,33 +283,84 @@ class QuantLinear(nn.Module):
 
 
 class Quant3Linear(QuantLinear):
-    def __init__(self, infeatures, outfeatures, faster=False):
-        super().__init__(3, infeatures, outfeatures, faster=faster)
+    def __init__(self, infeatures, outfeatures, faster=False, groupsize=-1):
+        super().__init__(3, infeatures, outfeatures, faster=faster, groupsize=groupsize)
 
 
 class Quant4Linear(QuantLinear):
-    def __init__(self, infeatures, outfeatures, faster=False):
-        super().__init__(4, infeatures, outfeatures, faster=faster)
+    """zeroShot/models/quant.py:162-200 (4-bit layout: code i of a column at bits 4*(i%8) of word i//8)."""
+
+    def __init__(self, infeatures, outfeatures, faster=False, groupsize=-1):
+        super().__init__(4, infeatures, outfeatures, faster=faster, groupsize=groupsize)
 
 
 class Quant2Linear(QuantLinear):
-    def __init__(self, infeatures, outfeatures, faster=False):
-        super().__init__(2, infeatures, outfeatures, faster=faster)
+    """2-bit layout by analogy with the 4-bit one (code << 2*(i%16)).  The reference defines NO 2-bit packed format, so this
+    layout is PARITY-UNPINNED by construction; only the integer codes are checked against the oracle."""
+
+    def __init__(self, infeatures, outfeatures, faster=False, groupsize=-1):
+        super().__init__(2, infeatures, outfeatures, faster=faster, groupsize=groupsize)
 
 
-def make_quant(module, names, bits, name="", faster=False):
+def make_quant(module, names, bits, name="", faster=False, groupsize=-1):
     if isinstance(module, QuantLinear):
         return
     for attr in dir(module):
         tmp = getattr(module, attr)
         name1 = name + "." + attr if name != "" else attr
         if name1 in names:
-            setattr(module, attr, QuantLinear(bits, tmp.in_features, tmp.out_features, faster=faster)
-                    if bits != 3 else Quant3Linear(tmp.in_features, tmp.out_features, faster=faster))
+            cls = {2: Quant2Linear, 3: Quant3Linear, 4: Quant4Linear}.get(bits)
+            setattr(module, attr, cls(tmp.in_features, tmp.out_features, faster=faster, groupsize=groupsize) if cls
+                    else QuantLinear(bits, tmp.in_features, tmp.out_features, faster=faster, groupsize=groupsize))
     for name1, child in module.named_children():
-        make_quant(child, names, bits, name + "." + name1 if name != "" else name1, faster=faster)
+        make_quant(child, names, bits, name + "." + name1 if name != "" else name1, faster=faster, groupsize=groupsize)
 
 
 def make_quant3(module, names, name="", faster=False):
     """quant.py:205-216."""
     make_quant(module, names, 3, name=name, faster=faster)
+
+
+def find_linears(module, kinds=(nn.Conv2d, nn.Linear), name=""):
+    """modelutils.py:8-16."""
+    if type(module) in kinds or (QuantLinear in kinds and isinstance(module, QuantLinear)):
+        return {name: module}
+    res = {}
+    for name1, child in module.named_children():
+        res.update(find_linears(child, kinds, name + "." + name1 if name != "" else name1))
+    return res
+
+
+def pack_model(model, quantizers, bits, extras=None, groupsize=-1, faster=False):
+    """opt.py:362-373 (opt_pack3) for any of the packed widths: replace every quantized linear by its packed layer.
+    `quantizers`: {name: Quantizer} as returned by the `*_sequential` driver.  The reference hands `pack` the quantizer's
+    [R,1] scale / zero, which is only meaningful for groupsize -1 (with groups it is the LAST group's pair, SURVEY 8a row J);
+    grouped models therefore pack from `extras[name]` = {"scales" [R,ng], "zeros" [R,ng], "g_idx" [K]} (the attributes
+    GPTQ.fasterquant leaves behind)."""
+    layers = find_linears(model)
+    layers = {n: layers[n] for n in quantizers}
+    make_quant(model, quantizers, bits, faster=faster, groupsize=groupsize)
+    qlayers = find_linears(model, (QuantLinear,))
+    for name in qlayers:
+        if name not in layers:
+            continue
+        ex = (extras or {}).get(name)
+        if ex is not None and ex.get("scales") is not None and ex["scales"].dim() == 2 and ex["scales"].shape[1] > 1:
+            qlayers[name].pack(layers[name], ex["scales"], ex["zeros"], g_idx=ex["g_idx"])
+        else:
+            q = quantizers[name]
+            qlayers[name].pack(layers[name], q.scale, q.zero)
+    return model
+
+
+def load_quant(model, checkpoint, bits, groupsize=-1, skip=("lm_head", "model.decoder.project_out", "model.decoder.project_in"),
+               faster=False):
+    """opt.py:375-402 (load_quant3) without the model construction: `model` is a freshly built (unquantized, any init)
+    model; its linears become packed layers and the checkpoint (a path or a state dict) is loaded strictly."""
+    layers = find_linears(model)
+    for name in skip:
+        layers.pop(name, None)
+    make_quant(model, layers, bits, faster=faster, groupsize=groupsize)
+    sd = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "read") else checkpoint
+    model.load_state_dict(sd)
+    return model

@@ -48,6 +48,9 @@ def find_layers(module, layers=(nn.Conv2d, nn.Linear), name=""):
 
 def decoder_parts(model):
     """(layers ModuleList, modules that must sit on the device while capturing, final norm / head pieces)."""
+    if hasattr(model, "transformer") and hasattr(model.transformer, "h"):          # BLOOM (bloom.py:25-60)
+        t = model.transformer
+        return t.h, [t.word_embeddings, t.word_embeddings_layernorm], [t.ln_f]
     m = model.model
     if hasattr(m, "decoder"):                      # OPT
         d = m.decoder
@@ -56,6 +59,16 @@ def decoder_parts(model):
         return d.layers, pre, post
     pre = [m.embed_tokens] + [x for x in (getattr(m, "rotary_emb", None),) if x is not None]   # Llama / Gemma
     return m.layers, pre, [m.norm]
+
+
+def layer_prefix(model) -> str:
+    if hasattr(model, "transformer") and hasattr(model.transformer, "h"):
+        return "transformer.h"
+    return "model.decoder.layers" if hasattr(model.model, "decoder") else "model.layers"
+
+
+class _StopForward(Exception):
+    """Raised by the last forward hook of a subset: the rest of the decoder layer is not needed for the Hessians."""
 
 
 LLAMA_SEQUENTIAL = [["self_attn.k_proj", "self_attn.v_proj", "self_attn.q_proj"], ["self_attn.o_proj"],
@@ -68,8 +81,9 @@ def _call_layer(layer, x, kwargs):
 
 
 @torch.no_grad()
-def capture_layer_inputs(model, tokens: torch.Tensor, dev):
-    """opt.py:37-76: run the embeddings on `dev`, stop at decoder layer 0, return (inps [N,S,H], kwargs)."""
+def capture_layer_inputs(model, tokens: torch.Tensor, dev, offload: bool = True):
+    """opt.py:37-76: run the embeddings on `dev`, stop at decoder layer 0, return (inps [N,S,H], kwargs).
+    `offload=False`: the model already lives on `dev` and stays there (no CPU round trips)."""
     layers, pre, _ = decoder_parts(model)
     use_cache = model.config.use_cache
     model.config.use_cache = False
@@ -95,9 +109,10 @@ def capture_layer_inputs(model, tokens: torch.Tensor, dev):
         except ValueError:
             pass
     layers[0] = layers[0].module
-    layers[0] = layers[0].cpu()
-    for p in pre:
-        p.cpu()
+    if offload:
+        layers[0] = layers[0].cpu()
+        for p in pre:
+            p.cpu()
     model.config.use_cache = use_cache
     kwargs = {k: v for k, v in cache["kwargs"].items() if k not in ("past_key_values", "past_key_value", "use_cache")}
     kwargs["use_cache"] = False
@@ -106,16 +121,49 @@ def capture_layer_inputs(model, tokens: torch.Tensor, dev):
 
 @torch.no_grad()
 def quantize_sequential(model, tokens: torch.Tensor, dev, args: QuantArgs, gptq_cls, quantizer_cls,
-                        quantize_fn: Optional[Callable] = None, log: Callable = lambda *a: None):
-    """The `*_sequential` loop.  Returns {layer-qualified linear name: quantizer} like the reference."""
+                        quantize_fn: Optional[Callable] = None, log: Callable = lambda *a: None,
+                        rank: int = 0, world: int = 1, group=None, offload: bool = True, early_exit: bool = False,
+                        stats: Optional[dict] = None, max_layers: int = 0):
+    """The `*_sequential` loop.  Returns {layer-qualified linear name: quantizer} like the reference.
+
+    Multi-GPU (`world` > 1, one process per GPU): every rank holds the model, forwards ITS calibration samples
+    (round-robin shard of `tokens`), the partial Hessians are summed by one all-reduce per distinct Hessian, every linear is
+    solved row-sharded and completed by one all-gather, and every rank re-forwards its own samples through the quantized
+    layer -- so the activations never leave the rank that produced them.
+    `early_exit`: a hooked pass stops once every linear of the subset has seen its input (the layer's own output is only
+    needed from the final pass, opt.py:216-217, which always runs in full) -- same results, fewer forward flops.
+    `stats`: if given, filled with wall-clock seconds per phase (a device synchronisation is inserted at the phase
+    boundaries when it is not None)."""
+    import time
+    from . import dist as gd
     layers, _, _ = decoder_parts(model)
-    inps, kwargs = capture_layer_inputs(model, tokens, dev)
+    if world > 1:
+        tokens = tokens[gd.sample_shard(tokens.shape[0], rank, world)]
+    n_total = None
+
+    def tick():
+        if stats is not None and torch.cuda.is_available():
+            torch.cuda.synchronize()
+        return time.perf_counter()
+
+    def add(name, t0):
+        if stats is not None:
+            stats[name] = stats.get(name, 0.0) + (tick() - t0)
+
+    t0 = tick()
+    inps, kwargs = capture_layer_inputs(model, tokens, dev, offload=offload)
+    add("capture_s", t0)
     outs = torch.zeros_like(inps)
     nsamples = inps.shape[0]
+    if world > 1:
+        cnt = torch.tensor([nsamples], device=inps.device, dtype=torch.int64)
+        gd.allreduce_sum_(cnt, group)
+        n_total = int(cnt.item())
     quantizers = {}
     extras = {}
-    prefix = "model.decoder.layers" if hasattr(model.model, "decoder") else "model.layers"
-    for i in range(len(layers)):
+    prefix = layer_prefix(model)
+    n_layers = len(layers) if not max_layers else min(max_layers, len(layers))
+    for i in range(n_layers):
         layer = layers[i].to(dev)
         full = find_layers(layer)
         if args.true_sequential and all(n in full for s in LLAMA_SEQUENTIAL for n in s):
@@ -138,26 +186,46 @@ def quantize_sequential(model, tokens: torch.Tensor, dev, args: QuantArgs, gptq_
                     quantizers[f"{prefix}.{i}.{name}"] = q
                 continue
 
+            fired = [0]
+
             def add_batch(name):
                 def tmp(_, inp, out):
                     gptq[name].add_batch(inp[0].data, out.data)
+                    fired[0] += 1
+                    if early_exit and fired[0] == len(subset):
+                        raise _StopForward
                 return tmp
             handles = [subset[name].register_forward_hook(add_batch(name)) for name in subset]
+            t0 = tick()
             for j in range(nsamples):
-                outs[j] = _call_layer(layer, inps[j].unsqueeze(0), kwargs)[0]
+                fired[0] = 0
+                try:
+                    outs[j] = _call_layer(layer, inps[j].unsqueeze(0), kwargs)[0]
+                except _StopForward:
+                    pass
+            add("forward_hessian_s", t0)
             for h in handles:
                 h.remove()
+            t0 = tick()
             for name in subset:
                 log(i, name)
-                gptq[name].fasterquant(blocksize=128, percdamp=args.percdamp, groupsize=args.groupsize,
-                                       actorder=args.act_order, static_groups=args.static_groups,
-                                       layer_name=f"{i}.{name}")
+                kw = dict(blocksize=128, percdamp=args.percdamp, groupsize=args.groupsize, actorder=args.act_order,
+                          static_groups=args.static_groups, layer_name=f"{i}.{name}")
+                if world > 1:
+                    gd.allreduce_hessian(gptq[name], group, total_samples=n_total)
+                    gd.fasterquant_sharded(gptq[name], group, **kw)
+                else:
+                    gptq[name].fasterquant(**kw)
                 quantizers[f"{prefix}.{i}.{name}"] = gptq[name].quantizer
                 extras[f"{prefix}.{i}.{name}"] = {k: getattr(gptq[name], k, None) for k in ("codes", "scales", "zeros", "g_idx", "error", "oracle_result")}
                 gptq[name].free()
+            add("solve_s", t0)
+        t0 = tick()
         for j in range(nsamples):
             outs[j] = _call_layer(layer, inps[j].unsqueeze(0), kwargs)[0]
-        layers[i] = layer.cpu()
+        add("reforward_s", t0)
+        if offload:
+            layers[i] = layer.cpu()
         del layer
         inps, outs = outs, inps
     return quantizers, extras

@@ -51,7 +51,9 @@ int64_t     gptq_b200_launch_count(void);
  *     of a TPC; tiles touching the lower triangle at 256 x 256 granularity), _CTA1 = the single-CTA kernel (M128 x N256).
  *     Both produce the same H up to fp32 summation order inside the tensor core.
  * ------------------------------------------------------------------------------------------ */
-enum { GPTQ_B200_SYRK_AUTO = 0, GPTQ_B200_SYRK_CTA1 = 1, GPTQ_B200_SYRK_CTA2 = 2 };
+enum { GPTQ_B200_SYRK_AUTO = 0 /* = _CTA2_BK128 */, GPTQ_B200_SYRK_CTA1 = 1, GPTQ_B200_SYRK_CTA2 = 2 /* 64-token stages x 6 */,
+       GPTQ_B200_SYRK_CTA2_BK128 = 3 /* 128-token stages x 3 */ };
+/* (bits 8-24 of `variant` carry tile-order / TMA tuning values for performance experiments; 0 = the shipped defaults) */
 size_t gptq_b200_syrk_workspace_bytes(int K, int64_t tokens, int variant);
 int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, int K, int64_t ldx,
                          float* H, int64_t ldh, float alpha, float beta, int chunk_tokens, int variant,
@@ -62,6 +64,10 @@ int gptq_b200_syrk_accum_simt(const void* X, int dtype, int64_t tokens, int K, i
                               float* H, int64_t ldh, float alpha, float beta, void* stream);
 /* H[i,j] <- H[j,i] for j > i (mirror the lower triangle). */
 int gptq_b200_symmetrize(float* H, int K, int64_t ldh, void* stream);
+/* Multi-GPU exchange #1: the all-reduce of the partial accumulators carries the lower triangle only.
+ * packed[r (r + 1) / 2 + c] = S[r][c], c <= r  (K (K + 1) / 2 floats); unpack writes the same entries back. */
+int gptq_b200_tril_pack(const float* S, int K, int64_t lds, float* packed, void* stream);
+int gptq_b200_tril_unpack(const float* packed, int K, float* S, int64_t lds, void* stream);
 /* Copy one calibration batch [tokens,K] (any ld) into a staging slab with ld_dst % 8 == 0. */
 int gptq_b200_stage_input(const void* src, int dtype, int64_t tokens, int K, int64_t ld_src,
                           void* dst, int64_t ld_dst, void* stream);

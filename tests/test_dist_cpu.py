@@ -55,11 +55,18 @@ def _worker(rank, world, port, rows):
         g = torch.Generator().manual_seed(rank)
         X = torch.randn(64, 16, generator=g)
         fake = _FakeGPTQ(X.t() @ X, 64 // 2 + rank)
+        mine = (X.t() @ X).clone()
         gd.allreduce_hessian(fake)
         want = sum((torch.randn(64, 16, generator=torch.Generator().manual_seed(r)).t()
                     @ torch.randn(64, 16, generator=torch.Generator().manual_seed(r))) for r in range(world))
-        assert torch.allclose(fake._S, want, atol=1e-5)
+        # only the lower triangle travels (the consumers mirror it): lower = global sum, strict upper = untouched
+        assert torch.allclose(torch.tril(fake._S), torch.tril(want), atol=1e-5)
+        assert torch.equal(torch.triu(fake._S, 1), torch.triu(mine, 1))
         assert fake.nsamples == sum(64 // 2 + r for r in range(world))
+        # a caller that knows the global sample count passes it: nothing is read back
+        fake2 = _FakeGPTQ(mine.clone(), 3)
+        gd.allreduce_hessian(fake2, total_samples=77)
+        assert fake2.nsamples == 77 and torch.allclose(torch.tril(fake2._S), torch.tril(want), atol=1e-5)
         # linears sharing one accumulator (same activations) are reduced ONCE; the siblings only pick up the global count
         class _Acc:
             reduced, count = False, 0
@@ -69,7 +76,7 @@ def _worker(rank, world, port, rows):
         a._acc = b._acc = acc
         gd.allreduce_hessian(a)
         gd.allreduce_hessian(b)
-        assert torch.allclose(S, want, atol=1e-5)                      # summed once, not twice
+        assert torch.allclose(torch.tril(S), torch.tril(want), atol=1e-5)   # summed once, not twice
         assert a.nsamples == b.nsamples == acc.count == sum(10 + r for r in range(world)) and acc.reduced
         # exchange #2: row shards (uneven on purpose)
         full = torch.arange(rows * 5, dtype=torch.float32).reshape(rows, 5)
@@ -78,6 +85,36 @@ def _worker(rank, world, port, rows):
         assert torch.equal(got, full)
         codes = (torch.arange(rows * 8) % 251).to(torch.uint8).reshape(rows, 8)
         assert torch.equal(gd.allgather_rows(codes[lo:hi].clone(), rows), codes)
+        # the row-sharded solve: every rank quantizes its rows, one exchange completes the layer on every rank
+        import torch.nn as nn
+        lin = nn.Linear(5, rows, bias=False)
+        Wq_full = (full / 7).half()
+        scales = torch.arange(rows * 2, dtype=torch.float32).reshape(rows, 2) + 1
+
+        class _Q:
+            scale = torch.zeros(1)
+            zero = torch.zeros(1)
+
+        class _Sharded:
+            def __init__(self):
+                self.layer, self.rows, self.quantizer = lin, rows, _Q()
+
+            def fasterquant(self, row_range=None, **kw):
+                a, b = row_range
+                self.Wq, self.codes = Wq_full[a:b].clone(), codes[a:b, :5].clone()
+                self.scales, self.zeros = scales[a:b].clone(), -scales[a:b].clone()
+                self._e = torch.tensor([float(b - a)], dtype=torch.float64)
+                self.quantizer.scale = scales[a:b, :1].clone()
+                self.quantizer.zero = scales[a:b, 1:].clone()
+
+            def error_tensor(self):
+                return self._e
+        sh = _Sharded()
+        gd.fasterquant_sharded(sh, blocksize=128)
+        assert torch.equal(sh.Wq, Wq_full) and torch.equal(lin.weight.data, Wq_full.float())
+        assert torch.equal(sh.codes, codes[:, :5]) and torch.equal(sh.scales, scales) and torch.equal(sh.zeros, -scales)
+        assert float(sh._error_dev) == float(rows)                     # sum of the shards' losses, each counted once
+        assert torch.equal(sh.quantizer.scale, scales[:, :1]) and torch.equal(sh.quantizer.zero, scales[:, 1:])
     finally:
         dist.destroy_process_group()
 

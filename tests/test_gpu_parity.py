@@ -195,8 +195,8 @@ def _syrk(X, K, kind, alpha=1.0, beta=0.0, H0=None, chunk=0):
     lib = _lib.load()
     T = X.shape[0]
     H = torch.zeros((K, K), device=DEV) if H0 is None else H0.clone()
-    if kind in ("tc", "tc1", "tc2"):
-        variant = {"tc": _lib.SYRK_AUTO, "tc1": _lib.SYRK_CTA1, "tc2": _lib.SYRK_CTA2}[kind]
+    if kind in ("tc", "tc1", "tc2", "tc3"):
+        variant = {"tc": _lib.SYRK_AUTO, "tc1": _lib.SYRK_CTA1, "tc2": _lib.SYRK_CTA2, "tc3": _lib.SYRK_CTA2_BK128}[kind]
         n = lib.gptq_b200_syrk_workspace_bytes(K, T, variant)
         ws = torch.empty(max(n, 16), dtype=torch.uint8, device=DEV)
         _lib.check(lib.gptq_b200_syrk_accum(X.data_ptr(), _lib.dt(X), T, K, X.stride(0), H.data_ptr(), K, alpha, beta, chunk,
@@ -215,7 +215,7 @@ def _acts(T, K, seed, dtype):
     return (torch.randn(T, K, generator=g) * chan).to(dtype)
 
 
-@pytest.mark.parametrize("kind", ["tc1", "tc2"])       # cta_group::1 (M128 x N256 per SM) and cta_group::2 (M256 x N256 per pair)
+@pytest.mark.parametrize("kind", ["tc1", "tc2", "tc3"])       # cta_group::1 (M128 x N256 per SM) and cta_group::2 (M256 x N256 per pair)
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("T,K", [(64, 64), (100, 200), (2048, 256), (2048, 768), (8192, 1024), (4096, 2048), (333, 136),
                                  (1000, 520), (640, 2312)])
@@ -257,7 +257,7 @@ def test_syrk_tc_alpha_beta_and_chunks():
     H0 = (H0 + H0.t()).to(DEV)
     want = 0.5 * H0.cpu().double() + 0.25 * (X.double().t() @ X.double())
     for chunk in (0, 64, 512, 4096):
-        for kind in ("tc1", "tc2"):
+        for kind in ("tc1", "tc2", "tc3"):
             got = _syrk(X.to(DEV), K, kind, alpha=0.25, beta=0.5, H0=H0, chunk=chunk)
             err = O.rel_fro(got.cpu(), want)
             _log(test="syrk_tc_alpha_beta", kind=kind, chunk=chunk, rel=err)
