@@ -411,6 +411,17 @@ def _copy_stream(dev):
 
 
 _H2D = {}
+_D2H = {}
+_LAYERS = {}
+
+
+def _d2h(dev, key, t):
+    """Queue a device-to-host copy of a result into a pinned buffer (allocated once per result); returns its bytes."""
+    buf = _D2H.get((dev, key))
+    if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
+        buf = _D2H[(dev, key)] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    return t.numel() * t.element_size()
 
 
 def _h2d_buffers(dev, nbytes, wbytes):
@@ -468,11 +479,13 @@ def _enqueue_subset_h2d(wl, dev, acts, weights, subset, slot, wrows=None):
         off = 0
         for li in subset:
             w = weights[li]
-            if wrows is not None:                          # row-sharded solve: this rank needs its own rows only
-                w = w[wrows[li][0]:wrows[li][1]]
             nb = w.numel() * w.element_size()
             wd = st["wbufs"][slot][off:off + nb].view(w.dtype).view(w.shape)
-            wd.copy_(w, non_blocking=True)
+            if wrows is not None:                          # row-sharded solve: this rank reads its own rows only (the rest of
+                lo, hi = wrows[li]                         # the layer's weight is produced by the all-gather)
+                wd[lo:hi].copy_(w[lo:hi], non_blocking=True)
+            else:
+                wd.copy_(w, non_blocking=True)
             wdev.append(wd)
             off += (nb + 255) // 256 * 256
         wev = torch.cuda.Event()
@@ -493,16 +506,26 @@ def quantize_layer(wl, dev, acts, weights, world, from_host, carry=None, prefetc
     pending = None
     subsets, linears = wl["subsets"], wl["linears"]
     rank = int(os.environ.get("RANK", "0"))
+    wrows = None
+    if world > 1:
+        wrows = {li: gd.shard_range(linears[li][1], rank, world) for li in range(len(linears))}
     if from_host:
         # `carry`: the previous step already queued this step's first subset behind its own last transfer
-        pending = carry if carry is not None else _enqueue_subset_h2d(wl, dev, acts, weights, subsets[0], 0)
+        pending = carry if carry is not None else _enqueue_subset_h2d(wl, dev, acts, weights, subsets[0], 0, wrows)
+    # the layer's modules exist before the step, like the model's in the reference drivers; only their weights are reset
+    mods = _LAYERS.get((id(wl), dev))
+    if mods is None:
+        mods = []
+        for name, r, c, a in linears:
+            lin = nn.Linear(c, r, bias=False, device="meta")
+            lin.to_empty(device=dev)
+            mods.append(lin.half())
+        _LAYERS[(id(wl), dev)] = mods
     for si, subset in enumerate(subsets):
         gs = []
         for li in subset:
             name, r, c, a = linears[li]
-            lin = nn.Linear(c, r, bias=False, device="meta")
-            lin.to_empty(device=dev)
-            lin = lin.half()
+            lin = mods[li]
             if not from_host:
                 lin.weight.data = weights[li].clone()
             g = GPTQ(lin)
@@ -516,7 +539,7 @@ def quantize_layer(wl, dev, acts, weights, world, from_host, carry=None, prefetc
             views, ready, wdev, wev = pending
             if si + 1 < len(subsets) or prefetch_next:      # the upload keeps running one subset ahead, across steps too
                 nxt = subsets[(si + 1) % len(subsets)]
-                pending = _enqueue_subset_h2d(wl, dev, acts, weights, nxt, (si + 1) & 1)
+                pending = _enqueue_subset_h2d(wl, dev, acts, weights, nxt, (si + 1) & 1, wrows)
             else:
                 pending = None
             for j in range(n_local):
@@ -543,9 +566,9 @@ def quantize_layer(wl, dev, acts, weights, world, from_host, carry=None, prefetc
                     qw = ql.qweight
                 else:
                     qw = pack_codes(g.codes, wl["wbits"])
-            if from_host:                                 # result back to the host: packed words + scales + zeros
-                outs = [qw.cpu(), g.scales.cpu(), g.zeros.cpu(), g.g_idx.cpu()]
-                d2h += sum(o.numel() * o.element_size() for o in outs)
+            if from_host:                                 # result back to pinned host memory: packed words + scales + zeros
+                for key, t in (("qw", qw), ("scales", g.scales), ("zeros", g.zeros), ("g_idx", g.g_idx)):
+                    d2h += _d2h(dev, (len(results), key), t)  # asynchronous; the step's closing synchronisation covers them
             results.append((qw, g))
             g.free()
         if from_host:                                     # activations staged, weights read: the landing area is free
@@ -737,7 +760,7 @@ def run_ours(args):
         if args.no_e2e:
             raise RuntimeError("skipped (--no-e2e)")
         acts_h, weights_h = make_inputs(wl, dev, rank, world, host=True)
-        h2d = sum(x.numel() * 2 for x in acts_h) + sum(w.numel() * 2 for w in weights_h)
+        h2d = sum(x.numel() * 2 for x in acts_h) + sum(w.numel() * 2 for w in weights_h) // world   # own samples + own weight rows
         e_steps = max(1, min(args.steps, 3))
         ems, _, _, _, d2h = timed(acts_h, weights_h, True, e_steps, 1, False)
         e2e = {"value": wl["weights"] / (ems / e_steps / 1e3) / 1e6, "unit": "Mweights/s", "h2d_bytes_per_step": h2d * world,

@@ -163,7 +163,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 ptx::mbar_wait(&conv_bar[stage], phase);
                 ptx::tc_fence_after();
-                const uint32_t sA = (ring + stage * GT_STAGE_BYTES) >> 4;
+                // (the descriptor's address field is 14 bits of the CTA-local offset: in a cluster -- split-K -- the shared
+                // address of a CTA with rank > 0 carries its rank in the high bits, which must not leak into the LBO field)
+                const uint32_t sA = ((ring + stage * GT_STAGE_BYTES) >> 4) & 0x3FFF;
                 const uint32_t sB = sA + ((2 * GT_A_BYTES) >> 4);
                 const uint32_t d_tmem = tmem_base + buf * GT_BN;
 #pragma unroll

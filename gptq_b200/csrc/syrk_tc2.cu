@@ -144,7 +144,7 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
             // descriptor = constant high part | (shared address >> 4): SWIZZLE_128B, LBO = panel, SBO = 1024, version 1
             constexpr uint64_t DESC_HI = ((uint64_t)((S2_PANEL >> 4) & 0x3FFF) << 16) | ((uint64_t)((1024 >> 4) & 0x3FFF) << 32) |
                                          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-            const uint32_t ring_lo = ptx::smem_u32(smem) >> 4;
+            const uint32_t ring_lo = (ptx::smem_u32(smem) >> 4) & 0x3FFF;      // 14-bit CTA-local offset field
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t bphase0 = 0, bphase1 = 0;
             for (int item = cid; item < n_items; item += ncl) {

@@ -75,6 +75,7 @@ GROUP_SIBLINGS = os.environ.get("GPTQ_B200_GROUP_SIBLINGS", "1") == "1"
 # together).  Measured on the power-capped B200 box: the 2.6 ms of hidden staging per layer are given back by lower
 # clocks in the kernels that follow (step time 112.3 ms either way), so the default stays single-stream.
 OVERLAP_SYRK = os.environ.get("GPTQ_B200_OVERLAP_SYRK", "0") == "1"
+RAMP_WINDOWS = os.environ.get("GPTQ_B200_RAMP_WINDOWS", "1") == "1"
 _SIDE_STREAMS = {}
 
 
@@ -92,10 +93,29 @@ PROFILE_FINE = False      # also time every staging copy / verification (hundred
 HOST_WAIT = None          # [seconds] accumulated host time blocked in fasterquant's record read-back, when set to a list
 
 
-class _prof:
+class _NoProf:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NOPROF = _NoProf()
+
+
+def _prof(name, work=0.0, meta=None, fine=False):
+    """Context manager timing a region with CUDA events when PROFILE is a list; a shared no-op object otherwise (the hot
+    add_batch path runs ~900 times per decoder layer)."""
+    if PROFILE is None or (fine and not PROFILE_FINE):
+        return _NOPROF
+    return _Prof(name, work, meta)
+
+
+class _Prof:
     def __init__(self, name, work=0.0, meta=None, fine=False):
         self.name, self.work, self.meta = name, work, meta
-        self.on = PROFILE is not None and (PROFILE_FINE or not fine)
+        self.on = True
 
     def __enter__(self):
         if self.on:
@@ -172,6 +192,7 @@ class _Accumulator:
         self.other_busy = None
         self.syrk_ev = None            # event: the last syrk launched on the side stream has finished
         self.staged = 0
+        self.ramp = 0                  # tokens after which the NEXT absorb flushes early (0 = only when the slab is full)
         self.ws = None
         self.count = 0                 # samples absorbed (the reference's nsamples)
         self.batches = 0
@@ -232,9 +253,15 @@ class _Accumulator:
             cap = max(tokens, 1) * max(STAGE_SAMPLES, 1)
             self.stage = torch.empty((cap, _round_up(K, 8)), device=self.dev, dtype=x.dtype)
             self.stage_other = self.stage_busy = self.other_busy = None
+            self.ramp = 2 * max(tokens, 1) if (RAMP_WINDOWS and K <= 8192 and STAGE_SAMPLES >= 8) else 0
         cap = self.stage.shape[0]
-        if tokens <= cap and self.staged + tokens > cap:
-            self.flush()                                   # keep a batch contiguous in the slab
+        if tokens <= cap and (self.staged + tokens > cap or self.staged >= self.ramp > 0):
+            # keep a batch contiguous in the slab.  The first windows of a calibration round are short (2, 4, 8 samples, then
+            # the full slab): after a host synchronisation (the previous linear's fasterquant) the device would otherwise
+            # idle until the host has staged a whole slab; the extra read-modify-write passes over S only pay for small K.
+            self.flush()
+            if self.ramp:
+                self.ramp = self.ramp * 2 if self.ramp * 2 < cap else 0
         in_slab = tokens <= cap
         if in_slab:                                        # the common case: no slicing, plain pointer arithmetic
             st_ = self.stage
@@ -838,17 +865,11 @@ class GPTQ:
                 sol = acc.solves[skey] = _solve_hessian(H, K, percdamp, actorder, dead=acc.dead)
             flag = acc.flag
             ent = acc.spec.pop(id(self), None)          # solved ahead by a sibling?
-            if ent is not None and ent[0] == argkey and not q.ready() and ent[1].shape == W.shape and ent[1].dtype == W.dtype:
-                # the weights the sibling solved for us must still be the layer's weights: compared on the device into the
-                # accumulator's flag, which is read with the single record below (no extra host sync)
-                if acc.flag is None:
-                    acc.flag = torch.zeros(1, device=dev, dtype=torch.int32)
-                    flag = acc.flag
-                if W.numel():
-                    esz = W.element_size() // 2     # compare_rows works on 16-bit units
-                    _lib.check(_lib.load().gptq_b200_compare_rows(W.data_ptr(), W.stride(0) * esz, ent[1].data_ptr(),
-                                                                  ent[1].stride(0) * esz, R, K * esz, acc.flag.data_ptr(),
-                                                                  _lib.stream()), "compare_rows")
+            # The result is used only if the weights the sibling solved for us are still the layer's weights, bit for bit;
+            # otherwise this linear is solved again (the reference would quantize whatever the layer holds now).  The
+            # comparison reads one flag back: the device is idle at this point (the sibling's fasterquant ended with its own
+            # read-back and nothing was queued since), so this costs a round trip, not a pipeline drain.
+            if ent is not None and ent[0] == argkey and not q.ready() and torch.equal(ent[1], W):
                 out = ent[2]
             sibs = [] if (out is not None or q.ready()) else self._siblings_to_solve_with(acc, argkey, R)
             del H
@@ -875,8 +896,7 @@ class GPTQ:
         self._release()
         if rec[1] != 0:
             raise RuntimeError("GPTQ: a batch assumed identical for linears sharing one Hessian accumulator differed "
-                               "(the tensor was modified between their forward hooks), or the weights of a linear solved "
-                               "together with a sibling changed before its own fasterquant; set GPTQ_B200_SHARE_H=0")
+                               "(the tensor was modified between their forward hooks); set GPTQ_B200_SHARE_H=0")
         bad = int(rec[0])
         if bad != 0:
             raise torch.linalg.LinAlgError(
@@ -907,7 +927,7 @@ class GPTQ:
         q_after = q
         if out["q_scale"] is not None:
             if static_groups:
-                q_after = copy.deepcopy(q)             # the reference swaps in groups[...] (a deepcopy), gptq.py:260
+                q_after = q.shallow_clone(copy_buffers=False)   # scale / zero are replaced right below; the reference swaps in groups[...] (a deepcopy), gptq.py:260
             q_after.scale, q_after.zero = out["q_scale"], out["q_zero"]
         self.quantizer = q_after
         if DEBUG:

@@ -148,6 +148,18 @@ class Quantizer(nn.Module):
             return quantize(x, self.scale, self.zero, self.maxq)
         return x
 
+    def shallow_clone(self, copy_buffers=True):
+        """A new Quantizer with the same configuration and buffers (what copy.deepcopy gives, without walking nn.Module)."""
+        q = Quantizer()
+        for k in ("wbits", "perchannel", "sym", "mse", "norm", "grid", "maxshrink", "trits"):
+            if hasattr(self, k):
+                setattr(q, k, getattr(self, k))
+        if copy_buffers:
+            q.maxq, q.scale, q.zero = self.maxq.clone(), self.scale.clone(), self.zero.clone()
+        else:
+            q.maxq, q.scale, q.zero = self.maxq, self.scale, self.zero
+        return q
+
     def enabled(self):
         return self.maxq > 0
 

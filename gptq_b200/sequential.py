@@ -217,7 +217,7 @@ def quantize_sequential(model, tokens: torch.Tensor, dev, args: QuantArgs, gptq_
                 else:
                     gptq[name].fasterquant(**kw)
                 quantizers[f"{prefix}.{i}.{name}"] = gptq[name].quantizer
-                extras[f"{prefix}.{i}.{name}"] = {k: getattr(gptq[name], k, None) for k in ("codes", "scales", "zeros", "g_idx", "error", "oracle_result")}
+                extras[f"{prefix}.{i}.{name}"] = {k: getattr(gptq[name], k, None) for k in ("codes", "scales", "zeros", "g_idx", "error", "perm", "oracle_result", "oracle_diag")}
                 gptq[name].free()
             add("solve_s", t0)
         t0 = tick()

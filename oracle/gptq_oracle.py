@@ -217,7 +217,8 @@ class FasterquantResult:
 
 def fasterquant(W: torch.Tensor, H: torch.Tensor, qp: QParams, blocksize: int = 128,
                 percdamp: float = .01, groupsize: int = -1, actorder: bool = False,
-                static_groups: bool = False, keep_U: bool = False, keep_margin: bool = False) -> FasterquantResult:
+                static_groups: bool = False, keep_U: bool = False, keep_margin: bool = False,
+                chain_fp64: bool = False, stable_perm: bool = False) -> FasterquantResult:
     """gptq.py:126-305, standard branch (lut_quant = non_linear_quant = columnwise = False).
 
     ``W`` [R,K] (any float dtype), ``H`` [K,K] fp32 as left by add_batch.  Both are cloned.
@@ -241,7 +242,11 @@ def fasterquant(W: torch.Tensor, H: torch.Tensor, qp: QParams, blocksize: int = 
 
     perm = None
     if actorder:                                            # gptq.py:165-169
-        perm = torch.argsort(torch.diag(H), descending=True)
+        # gptq.py:166 does not ask for a stable sort: EXACT ties in diag(H) (two channels with the same fp32 sum of squares;
+        # several dead columns with diag = 1) come out in an implementation-defined order that differs between torch's CPU
+        # sort (this line, what the golden vectors pin) and its CUDA radix sort (stable: ties keep ascending index, which is
+        # also what gptq_b200_argsort_desc produces).  `stable_perm` selects the latter for comparisons with the CUDA path.
+        perm = torch.argsort(torch.diag(H), descending=True, stable=stable_perm)
         W = W[:, perm]
         H = H[perm][:, perm]
         invperm = torch.argsort(perm)
@@ -251,7 +256,10 @@ def fasterquant(W: torch.Tensor, H: torch.Tensor, qp: QParams, blocksize: int = 
     C = torch.zeros_like(W)
     M = torch.full_like(W, 0.5) if keep_margin else None     # test instrumentation only; not part of the reference
 
-    Hinv = hinv_upper(H, percdamp)                          # gptq.py:174-180
+    if chain_fp64:      # CONTROL EXPERIMENT (tests only, not the reference): the exact factor, rounded once to fp32
+        Hinv = hinv_upper(H.double(), percdamp).float()
+    else:
+        Hinv = hinv_upper(H, percdamp)                      # gptq.py:174-180
     if not qp.ready():                                      # gptq.py:181-185
         qp.scale, qp.zero = find_params(W, qp)
 
@@ -452,30 +460,62 @@ def recon_error(W: torch.Tensor, Q: torch.Tensor, H: torch.Tensor) -> float:
     return float(torch.einsum("ik,kl,il->", d, H.double(), d))
 
 
-def classify_mismatches(codes: torch.Tensor, ref: "FasterquantResult", tol: float) -> dict:
+EXACT_TIE = 2.0 ** -20        # |frac(w/scale) - 0.5| below this: the tie is at the resolution of fp32 itself
+
+
+def classify_mismatches(codes: torch.Tensor, ref: "FasterquantResult", tol: float, perm: Optional[torch.Tensor] = None,
+                        diag: Optional[torch.Tensor] = None, perm_tol: float = 1e-5) -> dict:
     """Rounding-tie classifier for a run compared with the oracle run `ref` (which must carry `margin`).
 
     Rows are independent recurrences (gptq.py:191-276 acts row-wise), and inside a row everything after the first
     differing column legitimately differs (the error feedback of that column is different).  So a row's mismatches are
-    explained iff its FIRST differing column, in processing order (act-order permutation), was a rounding tie for the
-    oracle: |frac(w/scale) - 0.5| < tol, i.e. a perturbation of w/scale below `tol` flips round().  Returns counts;
-    `unexplained_rows` must be 0 and `mismatch_outside_tie_rows` (entries differing in rows without a tie) is then 0 too.
+    explained iff its FIRST differing column, in processing order (act-order permutation), was
+      * an exact rounding tie for the oracle: |frac(w/scale) - 0.5| < EXACT_TIE = 2^-20 (not reproducible by ANY fp32
+        implementation that reorders a sum), or
+      * a near tie: margin < `tol`, i.e. a perturbation of w/scale below `tol` quantization steps flips round(), or
+      * (act-order, when the other run's `perm` and diag(H) are given) at or after a SORT-KEY tie: the two runs process
+        different columns at some earlier-or-equal position and the diag(H) values being permuted there agree to `perm_tol`
+        relative -- the act-order argsort of gptq.py:166 is discontinuous at such ties, so Hessians equal to 1e-5 legitimately
+        give different processing orders, and from that position on the two runs are different (equally valid) GPTQ
+        solutions.  Positions where the orders differ WITHOUT such a tie are reported as `perm_unexplained_positions`.
+    `mismatch_outside_exact_tie_rows` is the code mismatch over the whole matrix when the tails of exact-tie rows are not counted.
     """
     assert ref.margin is not None, "run the oracle with keep_margin=True"
     a, b, m = codes.cpu(), ref.codes, ref.margin
+    swapped = torch.zeros(a.shape[1], dtype=torch.bool)
+    n_swapped = n_perm_bad = 0
     if ref.perm is not None:                      # original order -> processing order
         a, b, m = a[:, ref.perm], b[:, ref.perm], m[:, ref.perm]
+        if perm is not None:
+            pg = perm.cpu().long()
+            differs = pg != ref.perm
+            n_swapped = int(differs.sum())
+            if n_swapped and diag is not None:
+                d = diag.cpu().double()
+                close = (d[pg] - d[ref.perm]).abs() <= perm_tol * d[ref.perm].abs()
+                n_perm_bad = int((differs & ~close).sum())
+                if bool((differs & close).any()):
+                    swapped[int(torch.nonzero(differs & close)[0]):] = True       # everything from the first sort-key tie on
     diff = a != b
     bad_rows = torch.nonzero(diff.any(dim=1)).flatten()
     first = diff[bad_rows].to(torch.uint8).argmax(dim=1)
     fm = m[bad_rows, first] if len(bad_rows) else torch.zeros(0)
+    exact = fm < EXACT_TIE
     tie = fm < tol
-    unexplained = bad_rows[~tie]
-    outside = int(diff[unexplained].sum()) if len(unexplained) else 0
-    return dict(mismatch=float(diff.double().mean()), rows_bad=int(len(bad_rows)), tie_rows=int(tie.sum()),
-                unexplained_rows=int(len(unexplained)), mismatch_outside_tie_rows=outside,
-                max_first_margin=float(fm.max()) if len(fm) else 0.0,
-                first_margins=[float(x) for x in fm[:8]], tol=tol)
+    at_swap = swapped[first] if len(bad_rows) else torch.zeros(0, dtype=torch.bool)
+    explained = tie | at_swap
+    unexplained = bad_rows[~explained]
+    per_row = diff[bad_rows].sum(dim=1) if len(bad_rows) else torch.zeros(0, dtype=torch.int64)
+    unexp_m = fm[~explained]
+    return dict(mismatch=float(diff.double().mean()), rows_bad=int(len(bad_rows)), exact_tie_rows=int(exact.sum()),
+                tie_rows=int(tie.sum()), sort_key_tie_rows=int((at_swap & ~tie).sum()), perm_positions_differing=n_swapped,
+                perm_unexplained_positions=n_perm_bad,
+                unexplained_rows=int(len(unexplained)),
+                mismatch_outside_exact_tie_rows=float(per_row[~exact].sum()) / diff.numel() if len(bad_rows) else 0.0,
+                max_rounding_margin=float(fm[~at_swap | tie].max()) if len(fm) and bool((~at_swap | tie).any()) else 0.0,
+                max_unexplained_margin=float(unexp_m.max()) if len(unexp_m) else 0.0,
+                first_margins=[float(x) for x in sorted(fm.tolist(), reverse=True)[:6]],
+                first_cols=[int(first[i]) for i in (torch.argsort(fm, descending=True)[:6].tolist() if len(fm) else [])], tol=tol)
 
 
 def code_agreement(a: torch.Tensor, b: torch.Tensor) -> float:

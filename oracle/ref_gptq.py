@@ -49,8 +49,10 @@ class OracleGPTQ:
     def fasterquant(self, blocksize=128, percdamp=.01, groupsize=-1, actorder=False, static_groups=False, **_):
         W = self.layer.weight.data
         r = O.fasterquant(W.detach().cpu(), self.st.H, self.quantizer.qp, blocksize=blocksize, percdamp=percdamp,
-                          groupsize=groupsize, actorder=actorder, static_groups=static_groups, keep_margin=True)
+                          groupsize=groupsize, actorder=actorder, static_groups=static_groups, keep_margin=True,
+                          stable_perm=True)
         self.oracle_result = r                     # for the rounding-tie classifier of the tests
+        self.oracle_diag = torch.diag(self.st.H).clone()
         self.layer.weight.data = r.Q.to(W.dtype).to(W.device)
         self.codes, self.scales, self.zeros, self.g_idx, self.error = r.codes, r.scales, r.zeros, r.g_idx, r.error
         self.quantizer.scale, self.quantizer.zero = r.final_scale, r.final_zero

@@ -55,16 +55,19 @@ def test_sequential_quantization_matches_oracle(kind, qa):
     # Codes are comparable only where both runs saw IDENTICAL inputs, i.e. in decoder layer 0: from layer 1 on each run
     # calibrates on the outputs of its own quantized layers, so one legitimate rounding-tie flip upstream changes H.
     # Every differing row of layer 0 must start at a rounding tie of the oracle run (O.classify_mismatches); within the
-    # layer, a tie flip in an earlier subset perturbs the later subsets' Hessians (true-sequential), hence the gpu_H
-    # tolerance of tests/test_gpu_headline.py.
+    # layer, a tie flip in an earlier subset perturbs the later subsets' Hessians (true-sequential): only the linears of the
+    # FIRST subset (which see bit-identical inputs in both runs) are classified, with the gpu_H tolerance of
+    # tests/test_gpu_headline.py; the later ones are covered by the perplexity gate.
     from oracle import gptq_oracle as O
     tot = mism = tot_all = mism_all = rows_bad = unexplained = 0
     for k in ex_ref:
         a, b = ex_gpu[k]["codes"].cpu(), ex_ref[k]["codes"]
         tot_all += a.numel()
         mism_all += int((a != b).sum())
-        if ".layers.0." in k:
-            cls = O.classify_mismatches(a, ex_ref[k]["oracle_result"], 2.0 ** -8)
+        first_subset = (not qa.get("true_sequential")) or any(k.endswith(n) for n in S.LLAMA_SEQUENTIAL[0])
+        if ".layers.0." in k and first_subset:
+            cls = O.classify_mismatches(a, ex_ref[k]["oracle_result"], 2.0 ** -14, perm=ex_gpu[k].get("perm"),
+                                        diag=ex_ref[k]["oracle_diag"], perm_tol=1e-5)
             tot += a.numel()
             mism += int((a != b).sum())
             rows_bad += cls["rows_bad"]

@@ -33,9 +33,14 @@ if torch.cuda.is_available():
     from gptq_b200 import quant as Q
     DEV = torch.device("cuda:0")
 
-# A perturbation of w/scale below this flips round(): the two runs differ by the fp32 summation order of the inverse-Cholesky
-# chain and of the lazy-update GEMMs (same_H), plus the Hessian's 1e-6 relative difference (gpu_H); both stay well below it.
-TIE_TOL = {"same_H": 2.0 ** -10, "gpu_H": 2.0 ** -8}
+# |frac(w/scale) - 0.5| (in units of one quantization step) below which the first differing column of a row counts as a
+# rounding tie.  With identical H and identical processing order the CUDA solver differs from the oracle only at the
+# resolution of fp32 itself (measured on B200, profiles/r02_parity_headline.md: every first-divergence margin <= 4.8e-7, the
+# same rows the oracle flips against ITSELF when its factor is computed in fp64 -- the control below); 2^-18 leaves a factor
+# of 8.  With the Hessian from the tcgen05 syrk (~2e-6 relative from the reference's fp32 sgemm) the perturbation of w/scale
+# grows accordingly; 2^-14 of a step is the tolerance there.  Act-order adds sort-key ties (see O.classify_mismatches).
+TIE_TOL = {"same_H": 2.0 ** -18, "gpu_H": 2.0 ** -14}
+PERM_TOL = 1e-5          # relative agreement of two diag(H) values that may legitimately swap places in the act-order
 
 
 def _log(**kw):
@@ -83,22 +88,31 @@ def _check_case(cfg):
     t1 = time.time()
     ref = O.fasterquant(W16, Href, O.QParams(bits=cfg["bits"]), blocksize=cfg.get("blocksize", 128),
                         groupsize=cfg.get("groupsize", -1), actorder=cfg.get("actorder", False),
-                        static_groups=cfg.get("static_groups", False), keep_margin=True)
+                        static_groups=cfg.get("static_groups", False), keep_margin=True, stable_perm=True)
     t2 = time.time()
     rec_ref = O.recon_error(W16.float(), ref.Q, Href)
+    if cfg.get("control", False):
+        # control experiment: how reproducible is the REFERENCE under an fp32-level change of its own arithmetic?  Same
+        # oracle, same H, but the upper factor computed exactly (fp64) and rounded to fp32.
+        ctl = O.fasterquant(W16, Href, O.QParams(bits=cfg["bits"]), blocksize=cfg.get("blocksize", 128),
+                            groupsize=cfg.get("groupsize", -1), actorder=cfg.get("actorder", False),
+                            static_groups=cfg.get("static_groups", False), chain_fp64=True, stable_perm=True)
+        _log(test="headline_control_oracle_fp64_chain_vs_oracle", case=cfg["name"], **O.classify_mismatches(ctl.codes, ref, TIE_TOL["same_H"]))
     for mode in cfg.get("modes", ("same_H", "gpu_H")):
         lin, g = _gpu_run(W16, batches, cfg, Href if mode == "same_H" else None)
-        cls = O.classify_mismatches(g.codes, ref, TIE_TOL[mode])
+        cls = O.classify_mismatches(g.codes, ref, TIE_TOL[mode], perm=g.perm, diag=torch.diag(Href), perm_tol=PERM_TOL)
         rel_err = abs(g.error - ref.error) / abs(ref.error)
         rec_gpu = O.recon_error(W16.float(), lin.weight.data.cpu().float(), Href)
         _log(test="headline", case=cfg["name"], H=mode, err_gpu=g.error, err_ref=ref.error, recon_gpu=rec_gpu, recon_ref=rec_ref,
              oracle_hessian_s=round(t1 - t0, 1), oracle_solve_s=round(t2 - t1, 1), **cls)
-        assert cls["unexplained_rows"] == 0, (mode, cls)                 # mismatches only at rounding ties
-        assert cls["mismatch"] <= 1e-3, (mode, cls)                      # >= 99.9 % of the codes agree
+        assert cls["unexplained_rows"] == 0 and cls["perm_unexplained_positions"] == 0, (mode, cls)   # mismatches only at ties
+        # >= 99.9 % of the codes agree; the tail of a row whose first difference is an EXACT fp32 tie (margin < 2^-20: no
+        # implementation that reorders an fp32 sum reproduces it, the reference on another BLAS included) is not counted
+        assert cls["mismatch_outside_exact_tie_rows"] <= 1e-3, (mode, cls)
         assert rel_err <= 1e-2, (mode, rel_err)
         assert abs(rec_gpu - rec_ref) <= 1e-2 * rec_ref, (mode, rec_gpu, rec_ref)
         if cfg.get("actorder", False) and mode == "same_H":
-            assert torch.equal(g.perm.cpu().long(), ref.perm)
+            assert torch.equal(g.perm.cpu().long(), ref.perm)            # identical H -> identical order (ties by index)
         # the codes dequantise to the weights written into the layer
         s = g.scales[:, g.g_idx.long()]
         zr = g.zeros[:, g.g_idx.long()]
@@ -109,7 +123,7 @@ def _check_case(cfg):
 
 HEADLINE = [
     # BASELINE configs[2] (the metric's configuration): Llama-2-7B 4-bit g128 act-order static groups
-    dict(name="llama7b_q_proj_4096x4096", R=4096, K=4096, bits=4, groupsize=128, actorder=True, static_groups=True, samples=8),
+    dict(name="llama7b_q_proj_4096x4096", R=4096, K=4096, bits=4, groupsize=128, actorder=True, static_groups=True, samples=8, control=True),
     dict(name="llama7b_down_proj_512x11008", R=512, K=11008, bits=4, groupsize=128, actorder=True, static_groups=True, samples=12),
     # configs[3]: BLOOM-7b1 2-bit g64, dynamic groups -> the stale-W group fit of gptq.py:253-255 at K = 16384
     dict(name="bloom7b1_4h_to_h_512x16384_b2_g64", R=512, K=16384, bits=2, groupsize=64, samples=16),

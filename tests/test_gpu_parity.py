@@ -29,7 +29,7 @@ def _log(**kw):
 
 # |frac(w/scale) - 0.5| below which a rounding flip between the CUDA path and the oracle counts as a tie (see
 # tests/test_gpu_headline.py): same_H = both solvers see the oracle's Hessian, gpu_H = H from the tcgen05 syrk
-TIE_TOL = {"same_H": 2.0 ** -10, "gpu_H": 2.0 ** -8}
+TIE_TOL = {"same_H": 2.0 ** -18, "gpu_H": 2.0 ** -14}
 
 
 # ------------------------------------------------------------------------------------------ pack
@@ -361,19 +361,19 @@ def test_fasterquant_vs_oracle_medium(cfg):
         O.add_batch(st, b)
     qp = O.QParams(bits=cfg["bits"])
     ref = O.fasterquant(W16, st.H, qp, groupsize=cfg.get("groupsize", -1), actorder=cfg.get("actorder", False),
-                        static_groups=cfg.get("static_groups", False), keep_margin=True)
+                        static_groups=cfg.get("static_groups", False), keep_margin=True, stable_perm=True)
     for mode in ("same_H", "gpu_H"):
         lin, g = _run_gptq(W16, batches, cfg, H_override=st.H if mode == "same_H" else None)
         # rounding-tie classifier (oracle/gptq_oracle.py): a row may differ only from a column on where the oracle's
         # w/scale sat within TIE_TOL of a rounding boundary; everything outside such rows must be identical
-        cls = O.classify_mismatches(g.codes, ref, TIE_TOL[mode])
+        cls = O.classify_mismatches(g.codes, ref, TIE_TOL[mode], perm=getattr(g, "perm", None), diag=torch.diag(st.H))
         mism_q = float((lin.weight.data.cpu() != ref.Q.half()).double().mean())
         rel_err = abs(g.error - ref.error) / abs(ref.error)
         rec_gpu = O.recon_error(W16.float(), lin.weight.data.cpu().float(), st.H)
         rec_ref = O.recon_error(W16.float(), ref.Q, st.H)
         _log(test="fasterquant_medium", case=cfg["name"], H=mode, q_mismatch=mism_q, err_gpu=g.error, err_ref=ref.error,
              recon_gpu=rec_gpu, recon_ref=rec_ref, **cls)
-        assert cls["unexplained_rows"] == 0, (mode, cls)
+        assert cls["unexplained_rows"] == 0 and cls["perm_unexplained_positions"] == 0, (mode, cls)
         # at this reduced width one tie row alone is > 0.1 % of the entries, so the 99.9 % gate is applied to the full
         # shapes in test_gpu_headline.py; here ties must stay rare
         assert cls["tie_rows"] <= max(2, R // 100), (mode, cls)

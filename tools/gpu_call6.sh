@@ -1,0 +1,6 @@
+#!/bin/bash
+set -x
+timeout 1500 python -m pytest tests -m gpu -q -s --maxfail=20 > gpurun_out/r2_tests6.log 2>&1
+echo "pytest exit $?" >> gpurun_out/r2_tests6.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench6_n1.json 2> gpurun_out/r2_bench6_n1.err
+echo "bench exit $?" >> gpurun_out/r2_bench6_n1.err
