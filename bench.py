@@ -659,6 +659,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    STEP_MS = []
+
     def timed(acts, weights, from_host, steps, warmup, profile):
         quiet = io.StringIO()
         d2h = 0
@@ -673,12 +675,18 @@ def run_ours(args):
             e1 = torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
             e0.record()
+            marks = []
             for i in range(steps):
                 _, d2h, carry = quantize_layer(wl, dev, acts, weights, world, from_host, carry, prefetch_next=from_host and i + 1 < steps)
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append(ev)
             e1.record()
             barrier()
             wall = time.perf_counter() - t0
         ms = e0.elapsed_time(e1)
+        STEP_MS.clear()
+        STEP_MS.extend(round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 2) for i in range(steps))
         prof = G.PROFILE
         G.PROFILE = None
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -692,6 +700,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms, wall, launches, prof, _ = timed(acts, weights, False, args.steps, args.warmup, True)
+    step_ms_each = list(STEP_MS)
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms / args.steps
     value = wl["weights"] / (ms_step / 1e3) / 1e6
@@ -780,7 +789,7 @@ def run_ours(args):
                     "hessian_tflops_issued": syrk_tflops, "hessian_tflops_dense_equivalent": dense_equiv,
                     "roofline": roofline, "rooflines_other": others, "phase_ms_per_step": phase_ms,
                     "phase_breakdown_instrumented_step": fine, "clocks": clocks, "e2e": e2e,
-                    "gpu_launches": launches, "impl": "ours"})
+                    "gpu_launches": launches, "impl": "ours", "ms_each_step_rank0": step_ms_each})
         if parity is not None:
             out["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:

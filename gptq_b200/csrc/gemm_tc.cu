@@ -466,6 +466,10 @@ int gemm_fp32(int transa, int transb, int M, int N, int Kd, float alpha, const f
     // kernel (with split-K) from 512x512 on
     if (M <= g_small_gemm_max && N <= g_small_gemm_max && (int64_t)M * N < (int64_t)g_small_gemm_max * g_small_gemm_max)
         return sgemm_small_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, mode, st);
+    // (A CTA-pair variant of the tensor-core kernel -- cta_group::2, 256 x 256 tiles, each SM staging and splitting only its
+    // 128 rows of A and 128 columns of B -- was built and measured in round 2: 130 TFLOP/s at 4096^3 against 163 for this
+    // kernel, 87 against 100 at the 4096 x 3584 x 512 lazy update; the cross-CTA hand-off of the split operands costs more
+    // than the halved B traffic saves, so it was removed again.  profiles/r02_gemm_pair_negative.md keeps the numbers.)
     if (g_gemm_backend == 1 && gemm_tc_supported(A, lda, B, ldb, C, ldc))
         return gemm_tc_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, mode, st);
     return sgemm_launch(transa, transb, M, N, Kd, alpha, A, lda, B, ldb, beta, C, ldc, mode, st);

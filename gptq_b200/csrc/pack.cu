@@ -72,30 +72,52 @@ pack_kernel(const void* __restrict__ src_, int R, int K, int64_t ld, const float
         }
     } else {
         const T* src = static_cast<const T*>(src_);
-        // each thread converts 4 consecutive channels at a time: 64 x 128 / 4 = 2048 quads, 8 per thread
+        // each thread converts 8 consecutive channels of one row per step (one 16-byte load for 16-bit weights):
+        // 64 x 128 / 8 = 1024 octets, 4 per thread.  The (scale, zero) pair is reloaded only when the group changes --
+        // groups are runs of consecutive channels except for act-order with dynamic groups.
+        const bool vec16 = (sizeof(T) == 2) && ((ld & 7) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            int v = tid + it * 256;
-            int r = v >> 5, q4 = v & 31;
-            int gr = r0 + r, gk = k0 + q4 * 4;
-            uint32_t word = 0;
-            if (gr < R) {
+        for (int it = 0; it < 4; ++it) {
+            const int v = tid + it * 256;
+            const int r = v >> 4, q8 = v & 15;
+            const int gr = r0 + r, gk = k0 + q8 * 8;
+            uint32_t word[2] = {0u, 0u};
+            if (gr < R && gk < K) {
+                float w[8];
+                const T* p = src + (int64_t)gr * ld + gk;
+                bool loaded = false;
+                if constexpr (sizeof(T) == 2) {
+                    if (vec16 && gk + 8 <= K) {
+                        const uint4 raw = *reinterpret_cast<const uint4*>(p);
+                        const T* h = reinterpret_cast<const T*>(&raw);
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    int k = gk + b;
+                        for (int b = 0; b < 8; ++b) w[b] = to_f32<T>(h[b]);
+                        loaded = true;
+                    }
+                }
+                if (!loaded) {
+#pragma unroll
+                    for (int b = 0; b < 8; ++b) w[b] = (gk + b < K) ? to_f32<T>(p[b]) : 0.f;
+                }
+                int gcur = -1;
+                float sc = 1.f, zs = 0.f;
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const int k = gk + b;
                     if (k < K) {
-                        int g = g_idx ? g_idx[k] : 0;
-                        float s = scale[(int64_t)gr * ngroups + g];
-                        float z = zero[(int64_t)gr * ngroups + g];
-                        float w = to_f32<T>(src[(int64_t)gr * ld + k]);
-                        // quant.py:153: zeros*scales; quant.py:158: round((W + zeros)/scales)
-                        float c = rintf(__fdiv_rn(__fadd_rn(w, __fmul_rn(z, s)), s));
-                        int ci = (int)c;
-                        word |= ((uint32_t)ci & 0xFFu) << (8 * b);
+                        const int g = g_idx ? g_idx[k] : 0;
+                        if (g != gcur) {
+                            gcur = g;
+                            sc = scale[(int64_t)gr * ngroups + g];
+                            zs = __fmul_rn(zero[(int64_t)gr * ngroups + g], sc);      // quant.py:153: zeros * scales
+                        }
+                        const int ci = (int)rintf(__fdiv_rn(__fadd_rn(w[b], zs), sc)); // quant.py:158: round((W + zeros) / scales)
+                        word[b >> 2] |= ((uint32_t)ci & 0xFFu) << (8 * (b & 3));
                     }
                 }
             }
-            tile[r * PK_PITCH + q4] = word;
+            tile[r * PK_PITCH + q8 * 2] = word[0];
+            tile[r * PK_PITCH + q8 * 2 + 1] = word[1];
         }
     }
     __syncthreads();

@@ -8,7 +8,8 @@
 // HBM-bound (the packed matrix is read exactly once, coalesced along the output dimension).  A CTA owns
 // 128 output columns x 256 input channels: x slab in shared memory, each thread unpacks 32 codes per
 // `bits` words and accumulates sum(code*x) in fp32; scale / zero are applied per group of channels
-// (once per slab when scales are per-row), then one atomicAdd per (thread, slab) like the reference.
+// (once per 32-channel stream when the stream lies inside one group), then one atomicAdd per (thread, slab) like the
+// reference.  All packed words of a (column, slab) are loaded before the first is used.
 #include "common.cuh"
 
 namespace gq {
@@ -16,11 +17,11 @@ namespace gq {
 constexpr int VQ_COLS = 128;       // output columns per CTA (= threads)
 constexpr int VQ_SLAB = 256;       // input channels per CTA
 
+// 32 codes of one (column, 32-channel) stream from its BITS packed words (LSB-first bit stream, pack.cu).
 template <int BITS>
-__device__ __forceinline__ void unpack32(const int32_t* __restrict__ q, int64_t stride, uint32_t (&c)[32]) {
+__device__ __forceinline__ void unpack32(const uint32_t (&wd)[BITS], uint32_t (&c)[32]) {
     if constexpr (BITS == 3) {
-        const uint32_t w0 = (uint32_t)q[0], w1 = (uint32_t)q[stride], w2 = (uint32_t)q[2 * stride];
-        const uint64_t lo = (uint64_t)w0 | ((uint64_t)w1 << 32), hi = (uint64_t)w1 | ((uint64_t)w2 << 32);
+        const uint64_t lo = (uint64_t)wd[0] | ((uint64_t)wd[1] << 32), hi = (uint64_t)wd[1] | ((uint64_t)wd[2] << 32);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             const int off = 3 * j;
@@ -32,9 +33,8 @@ __device__ __forceinline__ void unpack32(const int32_t* __restrict__ q, int64_t 
         constexpr int PER = 32 / BITS;
 #pragma unroll
         for (int w = 0; w < BITS; ++w) {
-            const uint32_t v = (uint32_t)q[(int64_t)w * stride];
 #pragma unroll
-            for (int j = 0; j < PER; ++j) c[w * PER + j] = (v >> (BITS * j)) & ((1u << BITS) - 1u);
+            for (int j = 0; j < PER; ++j) c[w * PER + j] = (wd[w] >> (BITS * j)) & ((1u << BITS) - 1u);
         }
     }
 }
@@ -43,10 +43,21 @@ template <int BITS, typename TX>
 __global__ void __launch_bounds__(VQ_COLS)
 vecquant_kernel(const TX* __restrict__ x, const int32_t* __restrict__ qweight, int R, int K, const float* __restrict__ scales,
                 const float* __restrict__ zs, int ng, const int32_t* __restrict__ g_idx, int groupsize, float* __restrict__ y) {
+    constexpr int NG32 = VQ_SLAB / 32;           // 32-channel streams per slab
     __shared__ float xs[VQ_SLAB];
     __shared__ int gs_[VQ_SLAB];
     const int col = blockIdx.x * VQ_COLS + threadIdx.x;
     const int k0 = blockIdx.y * VQ_SLAB;
+    const int nwords = min(VQ_SLAB, K - k0) / 32;
+    // every packed word of this (column, slab) is requested before anything is consumed: one memory round trip per CTA
+    uint32_t wq[NG32][BITS];
+    if (col < R) {
+#pragma unroll
+        for (int g = 0; g < NG32; ++g)
+#pragma unroll
+            for (int w = 0; w < BITS; ++w)
+                wq[g][w] = (g < nwords) ? (uint32_t)__ldg(qweight + ((int64_t)((k0 / 32 + g) * BITS + w)) * R + col) : 0u;
+    }
     for (int i = threadIdx.x; i < VQ_SLAB; i += VQ_COLS) {
         const int k = k0 + i;
         xs[i] = (k < K) ? to_f32<TX>(x[k]) : 0.f;
@@ -55,29 +66,27 @@ vecquant_kernel(const TX* __restrict__ x, const int32_t* __restrict__ qweight, i
     __syncthreads();
     if (col >= R) return;
     float res = 0.f;
-    const int nwords = min(VQ_SLAB, K - k0) / 32;
-    for (int g = 0; g < nwords; ++g) {
+#pragma unroll
+    for (int g = 0; g < NG32; ++g) {
+        if (g >= nwords) break;
         uint32_t c[32];
-        unpack32<BITS>(qweight + ((int64_t)((k0 / 32 + g) * BITS)) * R + col, R, c);
+        unpack32<BITS>(wq[g], c);
         const float* xg = xs + g * 32;
         const int* gg = gs_ + g * 32;
-        if (ng == 1) {                       // per-row scales: fully unrolled, codes stay in registers
+        // one (scale, zero) pair for the 32 channels: per-row scales, or a group that covers the whole stream (group sizes
+        // that are multiples of 32 in channel order: everything except act-order with dynamic groups)
+        const int g0 = gg[0];
+        if (ng == 1 || g0 == gg[31]) {
             float acc = 0.f, sx = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { acc = fmaf((float)c[j], xg[j], acc); sx += xg[j]; }
-            res += scales[col] * acc - zs[col] * sx;
-            continue;
-        }
-        // runs of equal group index inside the 32 channels share one (scale, zero)
-        int j = 0;
-        while (j < 32) {
-            const int grp = gg[j];
-            float acc = 0.f, sx = 0.f;
-            int e = j;
-            while (e < 32 && gg[e] == grp) { acc = fmaf((float)c[e], xg[e], acc); sx += xg[e]; ++e; }
-            const float s = scales[(int64_t)col * ng + grp], z = zs[(int64_t)col * ng + grp];
-            res += s * acc - z * sx;
-            j = e;
+            res += scales[(int64_t)col * ng + g0] * acc - zs[(int64_t)col * ng + g0] * sx;
+        } else {                             // scattered groups: one table lookup per channel (static register indexing)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int64_t o = (int64_t)col * ng + gg[j];
+                res = fmaf(fmaf(scales[o], (float)c[j], -zs[o]), xg[j], res);
+            }
         }
     }
     atomicAdd(&y[col], res);

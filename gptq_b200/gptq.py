@@ -62,11 +62,13 @@ SHARE_H = os.environ.get("GPTQ_B200_SHARE_H", "1") == "1"
 # SHARE_VERIFY: "full" = every shared batch is compared in full; "1" (default) = the first VERIFY_FULL_BATCHES shared
 # batches of an accumulator are compared in full -- which proves that the module really hands ONE unmodified tensor to
 # these linears (a module that changed its input between two sibling hooks would do so in every forward) -- and later
-# batches are compared on every VERIFY_ROW_STRIDE-th row (the pointer / shape / stride / dtype identity and the
-# keep-alive reference are checked for every batch regardless); "0" = identity checks only.
+# batches are spot-checked: every VERIFY_BATCH_STRIDE-th shared batch is compared on every VERIFY_ROW_STRIDE-th row (the
+# pointer / shape / stride / dtype identity and the keep-alive reference are checked for EVERY batch regardless, on the host,
+# without a launch); "0" = identity checks only.
 SHARE_VERIFY = os.environ.get("GPTQ_B200_SHARE_VERIFY", "1")
 VERIFY_FULL_BATCHES = 2
 VERIFY_ROW_STRIDE = 16
+VERIFY_BATCH_STRIDE = 8
 # Linears that share a Hessian and are quantized with the same arguments are solved in ONE column loop (their rows
 # stacked): the loop is latency-bound, so three 4096-row linears cost little more than one.
 GROUP_SIBLINGS = os.environ.get("GPTQ_B200_GROUP_SIBLINGS", "1") == "1"
@@ -75,7 +77,10 @@ GROUP_SIBLINGS = os.environ.get("GPTQ_B200_GROUP_SIBLINGS", "1") == "1"
 # together).  Measured on the power-capped B200 box: the 2.6 ms of hidden staging per layer are given back by lower
 # clocks in the kernels that follow (step time 112.3 ms either way), so the default stays single-stream.
 OVERLAP_SYRK = os.environ.get("GPTQ_B200_OVERLAP_SYRK", "0") == "1"
-RAMP_WINDOWS = os.environ.get("GPTQ_B200_RAMP_WINDOWS", "1") == "1"
+# Opt-in: short first staging windows (2, 4, 8 samples) so the device starts earlier after a synchronisation.  Measured on
+# B200: the 1.5 ms of idle it removes per layer are paid back by the extra read-modify-write passes over S and the smaller
+# launches (syrk 35.7 -> 37.2 ms per layer), so the default stays one full slab per launch.
+RAMP_WINDOWS = os.environ.get("GPTQ_B200_RAMP_WINDOWS", "0") == "1"
 _SIDE_STREAMS = {}
 
 
@@ -296,6 +301,10 @@ class _Accumulator:
         Runs once per sample and sibling: no tensor slicing, plain pointer arithmetic."""
         if SHARE_VERIFY == "0":
             return
+        self.verified += 1
+        full = SHARE_VERIFY == "full" or self.verified <= VERIFY_FULL_BATCHES * max(self.members - 1, 1)
+        if not full and self.verified % VERIFY_BATCH_STRIDE:
+            return
         if self.flag is None:
             self.flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
         if x.stride(-1) != 1:
@@ -304,8 +313,7 @@ class _Accumulator:
         ld = st.stride(0)
         ref_ptr = st.data_ptr() + (self.staged - self.last_tokens) * ld * st.element_size()
         rows, ldx = x.shape[0], x.stride(0)
-        self.verified += 1
-        if SHARE_VERIFY != "full" and self.verified > VERIFY_FULL_BATCHES * max(self.members - 1, 1) and rows >= VERIFY_ROW_STRIDE:
+        if not full and rows >= VERIFY_ROW_STRIDE:
             rows, ldx, ld = rows // VERIFY_ROW_STRIDE, ldx * VERIFY_ROW_STRIDE, ld * VERIFY_ROW_STRIDE
         with _prof("verify", fine=True):
             rc = _lib.load().gptq_b200_compare_rows(x.data_ptr(), ldx, ref_ptr, ld, rows, self.K,

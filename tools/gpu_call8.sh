@@ -1,0 +1,13 @@
+#!/bin/bash
+set -x
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_headline.py -q -s -k "gemm3x or hinv or headline or chain" > gpurun_out/r2_tests8.log 2>&1
+echo "pytest exit $?" >> gpurun_out/r2_tests8.log
+timeout 300 python tools/perf_probe.py gemmpair hinv hinvbig > gpurun_out/r2_probe8.log 2>&1
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-gpu-baseline > gpurun_out/r2_bench8_n1.json 2> gpurun_out/r2_bench8_n1.err
+echo "bench exit $?" >> gpurun_out/r2_bench8_n1.err
+timeout 120 python tools/syrk_lab.py once > gpurun_out/r2_once8.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:syrk_tc2 -c 10 -o gpurun_out/r2_prof_syrk_final python tools/syrk_lab.py once > gpurun_out/r2_ncu_syrk_final.log 2>&1
+timeout 120 python tools/perf_probe.py hbm once > /dev/null 2>&1 && \
+timeout 600 ncu --set full --clock-control none -k regex:"pack_kernel|pack_weights|find_params_kernel|vecquant_kernel" -c 18 -o gpurun_out/r2_prof_hbm python tools/perf_probe.py hbm once > gpurun_out/r2_ncu_hbm.log 2>&1
+ls -la gpurun_out/*.ncu-rep
+echo done

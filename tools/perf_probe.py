@@ -13,7 +13,14 @@ DEV = torch.device("cuda:0")
 lib = _lib.load()
 
 
+ONCE = False          # "once" on the command line: every probe launches its kernel twice and skips the timing loop (ncu runs)
+
+
 def timeit(fn, warm=2, iters=5):
+    if ONCE:
+        fn(); fn()
+        torch.cuda.synchronize()
+        return 1.0, 1.0
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -113,6 +120,55 @@ def probe_pack(R, K, bits):
     print(json.dumps(dict(op="pack_codes", R=R, K=K, bits=bits, us=best * 1e3, gbs=byts / best / 1e6)))
 
 
+def probe_pack_weights(R, K, bits, gs=128):
+    """The reference's entry point (quant.py:152-187): fp16 dequantised weights + scales / zeros in, packed words out."""
+    ng = K // gs
+    scale = torch.rand(R, ng, device=DEV) * 0.01 + 0.005
+    zero = torch.randint(0, 2 ** bits, (R, ng), device=DEV).float()
+    gidx = (torch.arange(K, device=DEV) // gs).to(torch.int32)
+    codes = torch.randint(0, 2 ** bits, (R, K), device=DEV).float()
+    W = (scale[:, gidx.long()] * (codes - zero[:, gidx.long()])).half()
+    qw = torch.empty((K * bits // 32, R), dtype=torch.int32, device=DEV)
+
+    def run():
+        _lib.check(lib.gptq_b200_pack_weights(W.data_ptr(), _lib.dt(W), R, K, K, scale.data_ptr(), zero.data_ptr(), ng,
+                                              gidx.data_ptr(), bits, qw.data_ptr(), _lib.stream()), "pack_weights")
+    best, _ = timeit(run, warm=3, iters=10)
+    byts = R * K * (2 + bits / 8) + 8 * R * ng
+    print(json.dumps(dict(op="pack_weights", R=R, K=K, bits=bits, us=best * 1e3, gbs=byts / best / 1e6)))
+
+
+def probe_find_params(R, K, gs):
+    W = torch.randn(R, K, device=DEV) * 0.02
+    ng = 1 if gs == -1 else K // gs
+    scale = torch.empty(R, ng, device=DEV)
+    zero = torch.empty(R, ng, device=DEV)
+
+    def run():
+        _lib.check(lib.gptq_b200_find_params(W.data_ptr(), R, K, K, 0, K, gs if gs > 0 else K, 15, 0, 0, 2.4, 100, 0.8,
+                                             scale.data_ptr(), zero.data_ptr(), ng, 0, _lib.stream()), "find_params")
+    best, _ = timeit(run, warm=3, iters=10)
+    byts = 4.0 * R * K + 8.0 * R * ng
+    print(json.dumps(dict(op="find_params", R=R, K=K, groupsize=gs, us=best * 1e3, gbs=byts / best / 1e6)))
+
+
+def probe_vecquant(R, K, bits, gs=-1):
+    ng = 1 if gs == -1 else K // gs
+    qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (K * bits // 32, R), dtype=torch.int32, device=DEV)
+    scale = torch.rand(R, ng, device=DEV) * 0.01 + 0.005
+    zs = torch.rand(R, ng, device=DEV)
+    gidx = (torch.arange(K, device=DEV) // max(gs, 1)).to(torch.int32) if gs > 0 else None
+    x = torch.randn(K, device=DEV).half()
+    y = torch.zeros(R, device=DEV)
+
+    def run():
+        _lib.check(lib.gptq_b200_vecquant_matvec(x.data_ptr(), _lib.dt(x), qw.data_ptr(), R, K, bits, scale.data_ptr(), zs.data_ptr(),
+                                                 ng, _lib.ptr(gidx), 0, y.data_ptr(), _lib.stream()), "vecquant")
+    best, _ = timeit(run, warm=3, iters=10)
+    byts = R * K * bits / 8 + 2.0 * K + 4.0 * R + 8.0 * R * ng
+    print(json.dumps(dict(op="vecquant_matvec", R=R, K=K, bits=bits, groupsize=gs, us=best * 1e3, gbs=byts / best / 1e6)))
+
+
 def probe_sgemm(M, N, Kd):
     A = torch.randn(M, Kd, device=DEV); B = torch.randn(Kd, N, device=DEV); C = torch.zeros(M, N, device=DEV)
     for name, fn in (("sgemm", lib.gptq_b200_sgemm), ("gemm3x", lib.gptq_b200_gemm3x)):
@@ -124,6 +180,9 @@ def probe_sgemm(M, N, Kd):
 
 if __name__ == "__main__":
     what = sys.argv[1:] or ["syrk", "hinv", "colloop", "pack", "sgemm"]
+    if "once" in what:
+        ONCE = True
+        what.remove("once")
     if "syrk" in what:
         for variant in (1, 2):
             for K, T in ((4096, 32768), (4096, 2048), (11008, 32768), (768, 32768), (2048, 32768)):
@@ -156,3 +215,13 @@ if __name__ == "__main__":
     if "pack" in what:
         for bits in (2, 3, 4):
             probe_pack(4096, 11008, bits)
+    if "hbm" in what:          # the HBM-bound byte kernels at Llama-2-7B down_proj / gate_proj shapes (ncu: achieved GB/s)
+        probe_pack(4096, 11008, 4)
+        probe_pack(4096, 11008, 3)
+        probe_pack_weights(4096, 11008, 4)
+        probe_pack_weights(4096, 11008, 3, gs=11008)
+        probe_find_params(4096, 11008, 128)
+        probe_find_params(11008, 4096, -1)
+        probe_vecquant(11008, 4096, 3)
+        probe_vecquant(11008, 4096, 4, gs=128)
+        probe_vecquant(4096, 11008, 4, gs=128)

@@ -93,13 +93,16 @@ SWEEP = [(8, 9, 0), (8, 9, 1), (6, 12, 0), (12, 6, 0), (4, 18, 0), (18, 4, 0), (
 
 def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "sustained"
-    if what == "once":
-        for K in (4096, 11008):
-            for variant in (1, 2, 3):
-                fn = make_syrk(K, 32768, variant)
-                for _ in range(2):
-                    fn()
-                torch.cuda.synchronize()
+    if what == "once":          # every launch shape of the default bench, default kernel, 2 launches each (ncu: use the 2nd)
+        order = []
+        for K, T in ((4096, 4096), (4096, 8192), (4096, 16384), (4096, 32768), (11008, 32768)):
+            fn = make_syrk(K, T, 0)
+            for _ in range(2):
+                fn()
+                order.append([K, T])
+            torch.cuda.synchronize()
+        with open("gpurun_out/r2_syrk_once_order.json", "w") as f:
+            json.dump(order, f)
         return
     if what == "sweep":          # tile-order / TMA-promotion sweep of the pair kernel at K = 11008 (run under ncu for DRAM bytes)
         for sw, sh, p128 in SWEEP:
@@ -110,6 +113,24 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); fn(); b.record(); torch.cuda.synchronize()
             print(json.dumps(dict(sw=sw, sh=sh, p128=p128, ms=a.elapsed_time(b), tflops=issued_flops(11008, 32768) / a.elapsed_time(b) / 1e9)), flush=True)
+        return
+    if what == "l2":             # L2 prefetch distance of the producer (variant bits 25-29; 31 = off), both headline shapes
+        for K in (4096, 11008):
+            for dist in (31, 4, 8, 16):
+                for chunk in (0, 1024):
+                    fn = make_syrk(K, 32768, 3 | (dist << 25), chunk)
+                    for _ in range(3):
+                        fn()
+                    torch.cuda.synchronize()
+                    ts = []
+                    for _ in range(6):
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(); fn(); b.record(); torch.cuda.synchronize()
+                        ts.append(a.elapsed_time(b))
+                        time.sleep(0.05)
+                    ts.sort()
+                    print(json.dumps(dict(K=K, l2_ahead=0 if dist == 31 else dist, chunk=chunk or 512, ms_best=ts[0], ms_median=ts[3],
+                                          tflops_median=issued_flops(K, 32768) / ts[3] / 1e9)), flush=True)
         return
     secs = float(sys.argv[2]) if len(sys.argv) > 2 else 1.5
     variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2]
