@@ -695,10 +695,17 @@ def run_ours(args):
         return float(t.item()), wall, _lib.launch_count() - n0, prof, d2h
 
     # ---- device-resident run (value)
-    acts, weights = make_inputs(wl, dev, rank, world, host=False)
+    # The clock sampler (nvidia-smi in loop mode) is started BEFORE the inputs are generated: its start-up (NVML
+    # initialisation, device enumeration) takes driver locks for a few hundred milliseconds, which showed up as one 300 ms
+    # step inside the timed region when it was started right in front of it.
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    acts, weights = make_inputs(wl, dev, rank, world, host=False)
+    if rank == 0:
+        t_wait = time.perf_counter()
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+            time.sleep(0.05)
     ms, wall, launches, prof, _ = timed(acts, weights, False, args.steps, args.warmup, True)
     step_ms_each = list(STEP_MS)
     clocks = sampler.stop() if rank == 0 else None

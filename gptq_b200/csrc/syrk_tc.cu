@@ -349,9 +349,7 @@ static SyrkPlan make_plan(int K, int64_t T) {
 // syrk_tc2.cu: the CTA-pair (cta_group::2) kernel
 size_t syrk2_workspace_bytes(int K, int64_t tokens);
 int syrk2_launch(const CUtensorMap& tmap, int bk, int dtype, int64_t tokens, int K, float* H, int64_t ldh, float alpha, float beta,
-                 int chunk, int sw, int sh, int l2_ahead, void* ws, size_t ws_bytes, cudaStream_t st);
-
-constexpr int SY2_L2_AHEAD_DEFAULT = 0;      // set from the measurement in profiles/r02_syrk_l2_prefetch.md
+                 int chunk, int sw, int sh, void* ws, size_t ws_bytes, cudaStream_t st);
 
 static size_t syrk1_workspace_bytes(int K, int64_t tokens) {
     if (K <= 0 || tokens <= 0) return 0;
@@ -381,7 +379,6 @@ extern "C" int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, in
     // bit 24 = TMA L2 promotion 256 B instead of the pair kernel's 128 B (which read 10 % less DRAM at K = 11008)
     const int tune_sw = (variant >> 8) & 0xFF, tune_sh = (variant >> 16) & 0xFF;
     const int tune_p128 = ((variant & 0xFF) == GPTQ_B200_SYRK_CTA1) ? 0 : !((variant >> 24) & 1);
-    const int tune_l2 = (variant >> 25) & 0x1F;          // bits 25-29: L2 prefetch distance in stages (0 = default)
     variant &= 0xFF;
     GQ_ARG(variant >= GPTQ_B200_SYRK_AUTO && variant <= GPTQ_B200_SYRK_CTA2_BK128, 11, "variant must be one of GPTQ_B200_SYRK_*");
     if (tokens == 0) return 0;                 // beta handling for empty input is the caller's business
@@ -405,8 +402,7 @@ extern "C" int gptq_b200_syrk_accum(const void* X, int dtype, int64_t tokens, in
     if (cr != CUDA_SUCCESS) return set_err(1000 + (int)cr, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
     int chunk = chunk_tokens > 0 ? chunk_tokens : 512;
-    if (pair) return syrk2_launch(tmap, pair_bk, dtype, tokens, K, H, ldh, alpha, beta, chunk, tune_sw, tune_sh,
-                                  tune_l2 == 31 ? 0 : (tune_l2 ? tune_l2 : SY2_L2_AHEAD_DEFAULT), ws, ws_bytes, st);
+    if (pair) return syrk2_launch(tmap, pair_bk, dtype, tokens, K, H, ldh, alpha, beta, chunk, tune_sw, tune_sh, ws, ws_bytes, st);
 
     GQ_ONCE_PER_DEVICE(GQ_CUDA(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SY_SMEM)));
     SyrkParams p;

@@ -22,6 +22,8 @@
 //   warps 2-9 epilogue in both CTAs: drain this CTA's 128 rows x 256 columns (tcgen05.ld), add round-to-nearest into 128
 //            fp32 registers per thread (the tensor core's own accumulator truncates, so a chain is bounded at `chunk`
 //            tokens), release the TMEM buffer to the leader (remote mbarrier arrive), fold into H at the end of the item.
+// (An L2 prefetch of the producer's future panels, cp.async.bulk.prefetch.tensor 4 / 8 / 16 stages ahead, was measured 8-12 %
+// SLOWER at both headline shapes -- profiles/r02_syrk_tc2_ncu_full.md -- and removed.)
 // Tile order: 2-D chunks of sw x sh tiles (about one wave of clusters) so that the clusters running at the same time
 // share channel panels in L2.  Few tiles (small K): the token range is split across clusters and a second kernel sums
 // the partial tiles in a fixed order (deterministic, no atomics).
@@ -52,7 +54,6 @@ struct Syrk2Params {
     float* partial;             // [splits][n_tiles][256][256] when splits > 1
     uint32_t idesc;
     int sw, sh;                 // tile-order chunk: column blocks x row blocks
-    int l2_ahead;               // stages by which the producer's L2 prefetch runs ahead of its loads (0 = off)
 };
 
 // Valid tiles are (bi, bj) with bi >= bj.  Enumerated in chunks of sw column blocks x sh row blocks; inside a chunk column
@@ -122,15 +123,6 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
                 const int64_t t0 = (int64_t)split * p.tokens_per_split;
                 const int64_t t1 = min(t0 + p.tokens_per_split, p.T);
                 for (int64_t t = t0; t < t1; t += S2_BK) {
-                    if (p.l2_ahead > 0) {
-                        // the panels this CTA will load `l2_ahead` stages from now are requested into L2 already (the shared-
-                        // memory ring only covers 384 tokens; at K = 11008 a third of the loads miss L2)
-                        const int64_t tp = t + (int64_t)p.l2_ahead * S2_BK;
-                        if (tp < t1) {
-                            if (!diag) { ptx::tma_prefetch_2d(&tmap, ch_a, (int)tp); ptx::tma_prefetch_2d(&tmap, ch_a + 64, (int)tp); }
-                            ptx::tma_prefetch_2d(&tmap, ch_b, (int)tp); ptx::tma_prefetch_2d(&tmap, ch_b + 64, (int)tp);
-                        }
-                    }
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (rank == 0)      // bytes of BOTH CTAs land on this barrier
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], diag ? 2 * S2_OP_BYTES : 2 * S2_STAGE_BYTES);
@@ -354,7 +346,7 @@ size_t syrk2_workspace_bytes(int K, int64_t tokens) {
 }
 
 int syrk2_launch(const CUtensorMap& tmap, int bk, int dtype, int64_t tokens, int K, float* H, int64_t ldh, float alpha, float beta,
-                 int chunk, int sw, int sh, int l2_ahead, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 int chunk, int sw, int sh, void* ws, size_t ws_bytes, cudaStream_t st) {
     GQ_ONCE_PER_DEVICE({
         GQ_CUDA(cudaFuncSetAttribute(syrk_tc2_kernel<64, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
         GQ_CUDA(cudaFuncSetAttribute(syrk_tc2_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM));
@@ -372,7 +364,6 @@ int syrk2_launch(const CUtensorMap& tmap, int bk, int dtype, int64_t tokens, int
     // 72 tiles ~ one wave of 74 clusters.  ncu at K = 11008 (721 MB slab, profiles/r02_syrk_tile_order_sweep.md): 12 x 6 reads
     // 5.0 GB from DRAM, 8 x 9 5.6 GB, 6 x 12 5.2 GB, 4 x 18 5.9 GB, 43 x 2 8.0 GB; durations within 2 % of each other
     p.sw = sw ? sw : 12; p.sh = sh ? sh : 6;
-    p.l2_ahead = l2_ahead;
     const int n_items = pl.n_tiles * pl.splits;
     const int grid = 2 * (n_items < pl.clusters ? n_items : pl.clusters);
     if (bk == 128) syrk_tc2_kernel<128, 3><<<grid, S2_THREADS, S2_SMEM, st>>>(tmap, p);

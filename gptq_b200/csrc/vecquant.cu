@@ -46,6 +46,7 @@ vecquant_kernel(const TX* __restrict__ x, const int32_t* __restrict__ qweight, i
     constexpr int NG32 = VQ_SLAB / 32;           // 32-channel streams per slab
     __shared__ float xs[VQ_SLAB];
     __shared__ int gs_[VQ_SLAB];
+    __shared__ int uni[NG32];                    // 1 when the 32 channels of a stream share one group
     const int col = blockIdx.x * VQ_COLS + threadIdx.x;
     const int k0 = blockIdx.y * VQ_SLAB;
     const int nwords = min(VQ_SLAB, K - k0) / 32;
@@ -64,6 +65,15 @@ vecquant_kernel(const TX* __restrict__ x, const int32_t* __restrict__ qweight, i
         gs_[i] = (ng > 1 && k < K) ? (g_idx ? g_idx[k] : k / groupsize) : 0;
     }
     __syncthreads();
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int b = warp; b < NG32; b += VQ_COLS / 32) {
+            const bool same = gs_[b * 32 + lane] == gs_[b * 32];
+            const bool all = __all_sync(0xffffffffu, same);
+            if (lane == 0) uni[b] = all ? 1 : 0;
+        }
+    }
+    __syncthreads();
     if (col >= R) return;
     float res = 0.f;
 #pragma unroll
@@ -76,7 +86,7 @@ vecquant_kernel(const TX* __restrict__ x, const int32_t* __restrict__ qweight, i
         // one (scale, zero) pair for the 32 channels: per-row scales, or a group that covers the whole stream (group sizes
         // that are multiples of 32 in channel order: everything except act-order with dynamic groups)
         const int g0 = gg[0];
-        if (ng == 1 || g0 == gg[31]) {
+        if (ng == 1 || uni[g]) {
             float acc = 0.f, sx = 0.f;
 #pragma unroll
             for (int j = 0; j < 32; ++j) { acc = fmaf((float)c[j], xg[j], acc); sx += xg[j]; }

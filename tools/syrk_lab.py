@@ -114,24 +114,6 @@ def main():
             a.record(); fn(); b.record(); torch.cuda.synchronize()
             print(json.dumps(dict(sw=sw, sh=sh, p128=p128, ms=a.elapsed_time(b), tflops=issued_flops(11008, 32768) / a.elapsed_time(b) / 1e9)), flush=True)
         return
-    if what == "l2":             # L2 prefetch distance of the producer (variant bits 25-29; 31 = off), both headline shapes
-        for K in (4096, 11008):
-            for dist in (31, 4, 8, 16):
-                for chunk in (0, 1024):
-                    fn = make_syrk(K, 32768, 3 | (dist << 25), chunk)
-                    for _ in range(3):
-                        fn()
-                    torch.cuda.synchronize()
-                    ts = []
-                    for _ in range(6):
-                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        a.record(); fn(); b.record(); torch.cuda.synchronize()
-                        ts.append(a.elapsed_time(b))
-                        time.sleep(0.05)
-                    ts.sort()
-                    print(json.dumps(dict(K=K, l2_ahead=0 if dist == 31 else dist, chunk=chunk or 512, ms_best=ts[0], ms_median=ts[3],
-                                          tflops_median=issued_flops(K, 32768) / ts[3] / 1e9)), flush=True)
-        return
     secs = float(sys.argv[2]) if len(sys.argv) > 2 else 1.5
     variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2]
     smi = Smi()
