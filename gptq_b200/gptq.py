@@ -202,6 +202,8 @@ class _Accumulator:
         self.count = 0                 # samples absorbed (the reference's nsamples)
         self.batches = 0
         self.members = 1
+        self.raw_key = None            # identity of the hook's ORIGINAL tensor of the most recent batch (sibling fast path)
+        self.last_ld = 0
         self.key = None                # identity of the most recent batch ...
         self.ref = None                # ... and the tensor itself: while it is held its memory cannot be recycled
         self.first_key = None
@@ -296,9 +298,10 @@ class _Accumulator:
             done += n
         self.last_in_slab = False
 
-    def verify(self, x):
+    def verify(self, x, ldx=None):
         """Device-side proof that `x` is bit-identical to the batch staged last (result read at fasterquant's sync).
-        Runs once per sample and sibling: no tensor slicing, plain pointer arithmetic."""
+        Runs once per sample and sibling: no tensor slicing, plain pointer arithmetic.  `ldx`: row pitch when `x` is the
+        hook's original (possibly 3-D) tensor rather than its [tokens, K] view."""
         if SHARE_VERIFY == "0":
             return
         self.verified += 1
@@ -307,12 +310,14 @@ class _Accumulator:
             return
         if self.flag is None:
             self.flag = torch.zeros(1, device=self.dev, dtype=torch.int32)
-        if x.stride(-1) != 1:
-            x = x.contiguous()
+        if ldx is None:
+            if x.stride(-1) != 1:
+                x = x.contiguous()
+            ldx = x.stride(0)
         st = self.stage
         ld = st.stride(0)
         ref_ptr = st.data_ptr() + (self.staged - self.last_tokens) * ld * st.element_size()
-        rows, ldx = x.shape[0], x.stride(0)
+        rows = self.last_tokens
         if not full and rows >= VERIFY_ROW_STRIDE:
             rows, ldx, ld = rows // VERIFY_ROW_STRIDE, ldx * VERIFY_ROW_STRIDE, ld * VERIFY_ROW_STRIDE
         with _prof("verify", fine=True):
@@ -620,6 +625,18 @@ class GPTQ:
         if DEBUG:
             self.inp1 = inp
             self.out1 = out
+        acc = self._acc
+        if acc is not None and acc.members > 1 and acc.raw_key is not None and not self._consumed:
+            # Fast path of a sibling hook (q/k/v, gate/up: ~900 hook calls per decoder layer, and the device idles while the
+            # host works through them): the very tensor a sibling staged a moment ago -- same memory, shape, strides, dtype,
+            # still held alive by the accumulator -- needs no view, no staging and (mostly) no launch.
+            if (acc.raw_key == (inp.data_ptr(), inp.shape, inp.stride(), inp.dtype) and acc.last_in_slab
+                    and acc.count == self.nsamples + acc.last_tmp):
+                self._H = None
+                acc.verify(inp, acc.last_ld)
+                self.nsamples += acc.last_tmp
+                return
+        raw_key = (inp.data_ptr(), inp.shape, inp.stride(), inp.dtype) if (SHARE_H and self._is_linear) else None
         if not inp.is_cuda:
             _lib.require_cuda(inp, "GPTQ.add_batch: inp")
         if inp.dim() == 2:
@@ -668,6 +685,10 @@ class GPTQ:
                 acc = self._acc
         acc.absorb(x, tmp, key, shareable)
         self.nsamples += tmp
+        if shareable and raw_key is not None and x.stride(-1) == 1 and x.data_ptr() == raw_key[0] and acc.last_in_slab:
+            acc.raw_key, acc.last_ld = raw_key, x.stride(0)
+        else:
+            acc.raw_key = None
 
     def _fork(self):
         """Leave a shared accumulator, taking a private copy of the state that matches THIS object's history."""

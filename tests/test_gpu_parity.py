@@ -264,6 +264,26 @@ def test_syrk_tc_alpha_beta_and_chunks():
             assert err < 1e-5
 
 
+@pytest.mark.parametrize("K,ld", [(1, 4), (7, 8), (130, 136), (1000, 1000), (4096, 4096)])
+def test_tril_pack_unpack_roundtrip(K, ld):
+    """Multi-GPU exchange #1 carries the packed lower triangle (K (K + 1) / 2 floats): pack / unpack are exact inverses on
+    the lower triangle and never touch the strict upper triangle."""
+    lib = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(K)
+    S = torch.randn((K, ld), device=DEV, generator=g)
+    n = K * (K + 1) // 2
+    packed = torch.full((n + 3,), -7.0, device=DEV)
+    _lib.check(lib.gptq_b200_tril_pack(S.data_ptr(), K, ld, packed.data_ptr(), _lib.stream()), "tril_pack")
+    idx = torch.tril_indices(K, K, device=DEV)
+    assert torch.equal(packed[:n], S[idx[0], idx[1]])              # row-major over the lower triangle
+    assert torch.all(packed[n:] == -7.0)
+    out = torch.full((K, ld), 3.0, device=DEV)
+    _lib.check(lib.gptq_b200_tril_unpack(packed.data_ptr(), K, out.data_ptr(), ld, _lib.stream()), "tril_unpack")
+    want = torch.full((K, ld), 3.0, device=DEV)
+    want[idx[0], idx[1]] = S[idx[0], idx[1]]
+    assert torch.equal(out, want)
+
+
 def test_syrk_accumulation_bias_long():
     # long reduction (32768 tokens, all-positive diagonal): exposes tensor-core accumulator rounding
     T, K = 32768, 256

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -x
-timeout 600 python -m pytest tests/test_gpu_parity.py -q -k "quantlinear or pack" > gpurun_out/r2_tests10.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_api_edges.py -q -k "quantlinear or pack or tril or api_edges" > gpurun_out/r2_tests10.log 2>&1
 echo "pytest exit $?" >> gpurun_out/r2_tests10.log
 timeout 900 python bench.py --workload model --config llama7b > gpurun_out/r2_model_n1.json 2> gpurun_out/r2_model_n1.err
 echo "model exit $?" >> gpurun_out/r2_model_n1.err
