@@ -42,6 +42,7 @@ SIGNATURES = {
     "gptq_b200_hinv_upper_workspace_bytes": (_sz, [_i]),
     "gptq_b200_hinv_upper": (_i, [_vp, _i, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "gptq_b200_find_params": (_i, [_vp, _i, _i, _i64, _i, _i, _i, _i, _i, _i, _f, _i, _f, _vp, _vp, _i64, _i, _vp]),
+    "gptq_b200_dequant_codes": (_i, [_vp, _i64, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i64, _vp]),
     "gptq_b200_quantize": (_i, [_vp, _i, _i, _i64, _vp, _vp, _i64, _i64, _i, _vp, _i64, _vp]),
     "gptq_b200_colloop_workspace_bytes": (_sz, [_i, _i, _i]),
     "gptq_b200_colloop": (_i, [_vp, _i, _i, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i, _f,

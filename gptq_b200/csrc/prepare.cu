@@ -245,6 +245,26 @@ finalize_kernel(const float* __restrict__ Q, int64_t ldq, const uint8_t* __restr
     }
 }
 
+// ------------------------------------------------------------------ codes -> dequantised weights
+// w[r][c] = T(scale[r][g(c)] * (code[r][c] - zero[r][g(c)]))  -- quant.py:10 followed by the cast of gptq.py:305: exactly what
+// the column loop wrote for that weight, so a rank that received only the codes of another rank's rows (1 byte per weight
+// instead of 3) rebuilds bit-identical layer weights.  One CTA per row; 16 codes per thread per step.
+template <typename T>
+__global__ void __launch_bounds__(256)
+dequant_codes_kernel(const uint8_t* __restrict__ codes, int64_t ldc, int R, int K, const float* __restrict__ scale,
+                     const float* __restrict__ zero, int ng, const int32_t* __restrict__ gidx, T* __restrict__ wout, int64_t ldwo) {
+    for (int r = blockIdx.x; r < R; r += gridDim.x) {
+        const uint8_t* cd = codes + (int64_t)r * ldc;
+        const float* sr = scale + (int64_t)r * ng;
+        const float* zr = zero + (int64_t)r * ng;
+        T* wo = wout + (int64_t)r * ldwo;
+        for (int c = threadIdx.x; c < K; c += blockDim.x) {
+            const int g = (ng > 1) ? gidx[c] : 0;
+            wo[c] = from_f32<T>(dequant((float)cd[c], sr[g], zr[g]));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ quantize (quant.py:6-10)
 __global__ void quantize_kernel(const float* __restrict__ x, int R, int C, int64_t ldx, const float* __restrict__ scale,
                                 const float* __restrict__ zero, int64_t s_row, int64_t s_col, int maxq,
@@ -421,6 +441,21 @@ extern "C" int gptq_b200_finalize(const float* Q, int64_t ldq, const uint8_t* co
     if (dtype == GPTQ_B200_F16) finalize_kernel<__half><<<g, 256, 0, st>>>(Q, ldq, codes, ldc, R, K, invperm, (__half*)weight_out, ldwo, codes_out, ldco);
     else if (dtype == GPTQ_B200_BF16) finalize_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(Q, ldq, codes, ldc, R, K, invperm, (__nv_bfloat16*)weight_out, ldwo, codes_out, ldco);
     else finalize_kernel<float><<<g, 256, 0, st>>>(Q, ldq, codes, ldc, R, K, invperm, (float*)weight_out, ldwo, codes_out, ldco);
+    GQ_LAUNCHED();
+    return 0;
+}
+
+extern "C" int gptq_b200_dequant_codes(const uint8_t* codes, int64_t ldc, int R, int K, const float* scale, const float* zero,
+                                       int ngroups, const int32_t* g_idx, void* weight_out, int dtype, int64_t ldwo, void* stream) {
+    GQ_ARG(codes, 1, "null"); GQ_ARG(ldc >= K, 2, "ldc<K"); GQ_ARG(R >= 0, 3, "R<0"); GQ_ARG(K >= 0, 4, "K<0");
+    GQ_ARG(scale && zero, 5, "null"); GQ_ARG(ngroups >= 1, 7, "ngroups<1"); GQ_ARG(ngroups == 1 || g_idx, 8, "g_idx required when ngroups > 1");
+    GQ_ARG(weight_out, 9, "null"); GQ_ARG(dtype >= 0 && dtype <= 2, 10, "dtype"); GQ_ARG(ldwo >= K, 11, "ldwo<K");
+    if (R == 0 || K == 0) return 0;
+    const int g = R < 65535 ? R : 65535;
+    cudaStream_t st = as_stream(stream);
+    if (dtype == GPTQ_B200_F16) dequant_codes_kernel<__half><<<g, 256, 0, st>>>(codes, ldc, R, K, scale, zero, ngroups, g_idx, (__half*)weight_out, ldwo);
+    else if (dtype == GPTQ_B200_BF16) dequant_codes_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(codes, ldc, R, K, scale, zero, ngroups, g_idx, (__nv_bfloat16*)weight_out, ldwo);
+    else dequant_codes_kernel<float><<<g, 256, 0, st>>>(codes, ldc, R, K, scale, zero, ngroups, g_idx, (float*)weight_out, ldwo);
     GQ_LAUNCHED();
     return 0;
 }

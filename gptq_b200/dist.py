@@ -6,8 +6,9 @@ The path shards along two axes with exactly one exchange each (BASELI
    all-reduce(sum) makes H identical on every rank.  Only the lower triangle travels (K (K + 1) / 2 floats, packed by a
    kernel), and the sample count rides in the same buffer, so the exchange is one collective and no host round trip.
 2. W rows -> independent column loops: given the (replicated) inverse-Cholesky factor, rows of W are independent, so rank g
-   quantizes rows [r0, r1) and ONE coalesced all-gather (a single NCCL group launch: dequantised weights, codes, scales,
-   zeros, per-shard loss) completes the layer.
+   quantizes rows [r0, r1) and ONE coalesced all-gather (a single NCCL group launch: codes, scales, zeros, per-shard loss --
+   1 byte per weight; the dequantised fp16 weights of the other ranks' rows are rebuilt from the codes, bit for bit)
+   completes the layer.
 
 The collectives are torch.distributed calls (NCCL over NVLink on the GPU box, gloo in the CPU tests); nothing here touches
 the arithmetic.
@@ -146,14 +147,36 @@ def fasterquant_sharded(gptq, group=None, **kw):
     q = gptq.quantizer
     per_row_q = q.scale.shape[0] == hi - lo and q.scale.dim() >= 1 and q.scale.numel() % max(hi - lo, 1) == 0 and hi - lo != R
     loss = gptq.error_tensor().reshape(1, 1).expand(hi - lo, 1).contiguous() if hi > lo else gptq.error_tensor().new_zeros((0, 1))
-    parts = [gptq.Wq, gptq.codes, gptq.scales, gptq.zeros, loss]
+    # Codes, scales and zeros determine the dequantised weights bit for bit (quant.py:10 + the cast of gptq.py:305), so the
+    # exchange carries 1 byte per weight instead of 3: every rank rebuilds the other ranks' rows from their codes
+    # (gptq_b200_dequant_codes).  The ternary grid (maxq < 0) has no such closed form here and ships its weights.
+    maxq = getattr(gptq, "_maxq", None)        # python int recorded by fasterquant (q.maxq may live on the device)
+    rebuild = gptq.codes.is_cuda and maxq is not None and maxq > 0 and getattr(gptq, "g_idx", None) is not None
+    parts = [gptq.codes, gptq.scales, gptq.zeros, loss]
+    if not rebuild:
+        parts.append(gptq.Wq)
     if per_row_q:
         parts += [q.scale.reshape(hi - lo, -1), q.zero.reshape(hi - lo, -1)]
     with _prof("nccl_allgather"):
         got = allgather_rows_multi(parts, R, group)
-    Wq, gptq.codes, gptq.scales, gptq.zeros, losses = got[:5]
-    if per_row_q:
-        q.scale, q.zero = got[5], got[6]
+        gptq.codes, gptq.scales, gptq.zeros, losses = got[:4]
+        nxt = 4
+        if rebuild:
+            from . import _lib
+            Wq = torch.empty((R, gptq.columns), device=gptq.codes.device, dtype=gptq.Wq.dtype)
+            sc, zr = gptq.scales.contiguous(), gptq.zeros.contiguous()
+            gi = gptq.g_idx.to(torch.int32).contiguous()
+            with torch.cuda.device(Wq.device):
+                _lib.check(_lib.load().gptq_b200_dequant_codes(gptq.codes.data_ptr(), gptq.codes.stride(0), R, gptq.columns,
+                                                               sc.data_ptr(), zr.data_ptr(), sc.shape[1], gi.data_ptr(), Wq.data_ptr(),
+                                                               _lib.dt(Wq), Wq.stride(0), torch.cuda.current_stream().cuda_stream),
+                           "dequant_codes")
+            Wq[lo:hi] = gptq.Wq                    # (own rows: identical by construction; keeps the solver's own output authoritative)
+        else:
+            Wq = got[nxt]
+            nxt += 1
+        if per_row_q:
+            q.scale, q.zero = got[nxt], got[nxt + 1]
     # one loss value per shard was replicated over the shard's rows: pick the first row of every shard, sum in rank order
     firsts = [shard_range(R, r, world)[0] for r in range(world) if shard_range(R, r, world)[1] > shard_range(R, r, world)[0]]
     gptq._error_dev = losses[firsts, 0].double().sum()

@@ -942,6 +942,7 @@ class GPTQ:
             else:
                 Wfull = Wout
             self.layer.weight.data = Wfull.reshape(self.layer.weight.shape)
+        self._maxq = qcfg[0]
         self.Wq = Wout                                  # [rows(shard), K] dequantised weights in the layer dtype
         self.codes = out["codes"]
         self.scales = out["scale"]

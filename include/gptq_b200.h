@@ -125,6 +125,12 @@ int gptq_b200_find_params(const float* W, int R, int K, int64_t ldw, int col0, i
                           int groupsize, int maxq, int sym, int mse, float norm, int grid,
                           float maxshrink, float* scale, float* zero, int64_t ldsz, int gout0,
                           void* stream);
+/* Dequantised weights from integer codes: out[r][c] = T(scale[r][g(c)] * (code[r][c] - zero[r][g(c)])) (quant.py:10 and the cast
+ * of gptq.py:305) -- bit-identical to what the column loop wrote for those codes.  Multi-GPU exchange #2 ships codes (1 byte per
+ * weight) and every rank rebuilds the other ranks' rows with this. */
+int gptq_b200_dequant_codes(const uint8_t* codes, int64_t ldc, int R, int K, const float* scale,
+                            const float* zero, int ngroups, const int32_t* g_idx,
+                            void* weight_out, int dtype, int64_t ldwo, void* stream);
 /* quant.py:6-10 elementwise: out = scale*(clamp(round(x/scale)+zero,0,maxq)-zero).
  * scale/zero index = r*s_row + c*s_col (so [R,1] -> (1,0); per-tensor -> (0,0); [1,C] -> (0,1)). */
 int gptq_b200_quantize(const float* x, int R, int C, int64_t ldx, const float* scale,

@@ -264,6 +264,26 @@ def test_syrk_tc_alpha_beta_and_chunks():
             assert err < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("grouped", [False, True])
+def test_dequant_codes_rebuilds_the_written_weights(grouped, dtype):
+    """Multi-GPU exchange #2 ships codes only: scale * (code - zero), cast to the layer dtype, must be bit-identical to the
+    weights the column loop writes (quant.py:10, gptq.py:305)."""
+    lib = _lib.load()
+    R, K, gs = 70, 328, 41
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ng = (K + gs - 1) // gs if grouped else 1
+    codes = torch.randint(0, 16, (R, K), device=DEV, dtype=torch.uint8, generator=g)
+    scale = torch.rand((R, ng), device=DEV, generator=g) * 0.02 + 0.003
+    zero = torch.randint(0, 16, (R, ng), device=DEV, generator=g).float()
+    gidx = (torch.randperm(K, device=DEV, generator=g) // gs).to(torch.int32) if grouped else torch.zeros(K, device=DEV, dtype=torch.int32)
+    out = torch.empty((R, K), device=DEV, dtype=dtype)
+    _lib.check(lib.gptq_b200_dequant_codes(codes.data_ptr(), K, R, K, scale.data_ptr(), zero.data_ptr(), ng, gidx.data_ptr(),
+                                           out.data_ptr(), _lib.dt(out), K, _lib.stream()), "dequant_codes")
+    want = (scale[:, gidx.long()] * (codes.float() - zero[:, gidx.long()])).to(dtype)
+    assert torch.equal(out, want)
+
+
 @pytest.mark.parametrize("K,ld", [(1, 4), (7, 8), (130, 136), (1000, 1000), (4096, 4096)])
 def test_tril_pack_unpack_roundtrip(K, ld):
     """Multi-GPU exchange #1 carries the packed lower triangle (K (K + 1) / 2 floats): pack / unpack are exact inverses on
