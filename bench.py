@@ -668,6 +668,7 @@ def run_ours(args):
         quiet = io.StringIO()
         d2h = 0
         with contextlib.redirect_stdout(quiet):
+            G.PROFILE = [] if profile else None        # the warm-up runs exactly what the timed steps run (event pools included)
             for _ in range(warmup):
                 quantize_layer(wl, dev, acts, weights, world, from_host)
             carry = None

@@ -75,6 +75,30 @@ __device__ __forceinline__ void decode_tile2(int t, int nb, int sw, int sh, int&
     bi = nb - 1; bj = 0;          // unreachable for t < n_tiles
 }
 
+// The same enumeration as decode_tile2, walked forward: a role of a cluster visits tiles cid, cid + ncl, ... in increasing order,
+// so the position is carried from item to item instead of being searched from the start (decode_tile2 costs O(chunks x sw)
+// iterations per call: 3 us at K = 11008, but ~25 us at K = 36864 -- OPT-66B fc2, 10 440 tiles -- on the producer's critical path).
+struct TileWalk2 {
+    int nb, sw, sh, sc, r0, j, base;
+    __device__ __forceinline__ void init(int nb_, int sw_, int sh_) { nb = nb_; sw = sw_; sh = sh_; sc = 0; r0 = 0; j = 0; base = 0; }
+    __device__ __forceinline__ void seek(int t, int& bi, int& bj) {          // t must not decrease between calls
+        for (;;) {
+            const int w = min(sw, nb - sc);
+            const int r1 = min(r0 + sh, nb);
+            const int lo = max(r0, j);
+            const int cnt = r1 - lo;
+            if (cnt > 0) {
+                if (t < base + cnt) { bj = j; bi = lo + (t - base); return; }
+                base += cnt;
+            }
+            if (++j >= sc + w) {
+                r0 += sh; j = sc;
+                if (r0 >= nb) { sc += sw; r0 = sc; j = sc; if (sc >= nb) { bi = nb - 1; bj = 0; return; } }
+            }
+        }
+    }
+};
+
 template <int S2_BK, int S2_STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(S2_THREADS, 1)
 syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
@@ -115,9 +139,10 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
         if (lane == 0) {
             const uint32_t full0 = ptx::mapa(ptx::smem_u32(&full_bar[0]), 0);      // the leader's full barriers
             int stage = 0; uint32_t phase = 0;
+            TileWalk2 walk; walk.init(p.nb, p.sw, p.sh);
             for (int item = cid; item < n_items; item += ncl) {
                 const int tile = item / p.splits, split = item - tile * p.splits;
-                int bi, bj; decode_tile2(tile, p.nb, p.sw, p.sh, bi, bj);
+                int bi, bj; walk.seek(tile, bi, bj);
                 const bool diag = bi == bj;
                 const int ch_a = bi * S2_T + (int)rank * 128, ch_b = bj * S2_T + (int)rank * 128;
                 const int64_t t0 = (int64_t)split * p.tokens_per_split;
@@ -149,9 +174,10 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
             const uint32_t ring_lo = (ptx::smem_u32(smem) >> 4) & 0x3FFF;      // 14-bit CTA-local offset field
             int stage = 0; uint32_t phase = 0;
             int buf = 0; uint32_t bphase0 = 0, bphase1 = 0;
+            TileWalk2 walk; walk.init(p.nb, p.sw, p.sh);
             for (int item = cid; item < n_items; item += ncl) {
                 const int tile = item / p.splits, split = item - tile * p.splits;
-                int bi, bj; decode_tile2(tile, p.nb, p.sw, p.sh, bi, bj);
+                int bi, bj; walk.seek(tile, bi, bj);
                 const uint32_t a_off_lo = (bi == bj) ? (S2_OP_BYTES >> 4) : 0;       // diagonal: A is this CTA's B half
                 const int64_t t0 = (int64_t)split * p.tokens_per_split;
                 const int64_t t1 = min(t0 + p.tokens_per_split, p.T);
@@ -191,9 +217,10 @@ syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, const Syrk2Params p) {
         int buf = 0; uint32_t bphase[2] = {0, 0};
         const bool hvec = ((p.ldh & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.H) & 15) == 0);
         const uint32_t tempty0 = ptx::mapa(ptx::smem_u32(&tempty_bar[0]), 0);
+        TileWalk2 walk; walk.init(p.nb, p.sw, p.sh);
         for (int item = cid; item < n_items; item += ncl) {
             const int tile = item / p.splits, split = item - tile * p.splits;
-            int bi, bj; decode_tile2(tile, p.nb, p.sw, p.sh, bi, bj);
+            int bi, bj; walk.seek(tile, bi, bj);
             // the strictly-upper 128 x 128 quarter of a diagonal tile is not needed (the consumers mirror the lower triangle)
             const bool need = !(bi == bj && rank == 0 && half == 1);
             const int64_t t0 = (int64_t)split * p.tokens_per_split;

@@ -66,3 +66,46 @@ def syrk_tile_order(nbm, sw=12, sh=12):
                 for bi in range(lo, r1):
                     out.append((bi, j))
     return out
+
+
+def syrk2_tile_order(nb, sw=12, sh=6):
+    """Python restatement of decode_tile2() in csrc/syrk_tc2.cu: the order in which the CTA-pair Hessian kernel walks the
+    256 x 256 tiles (bi, bj) with bi >= bj -- chunks of sw column blocks x sh row blocks, column by column inside a chunk."""
+    out = []
+    for sc in range(0, nb, sw):
+        w = min(sw, nb - sc)
+        for r0 in range(sc, nb, sh):
+            r1 = min(r0 + sh, nb)
+            for j in range(sc, sc + w):
+                for bi in range(max(r0, j), r1):
+                    out.append((bi, j))
+    return out
+
+
+class Syrk2TileWalk:
+    """Python restatement of TileWalk2 in csrc/syrk_tc2.cu: the same enumeration walked FORWARD (seek(t) with non-decreasing t),
+    so that a cluster visiting tiles cid, cid + ncl, ... does not search from the start for every item."""
+
+    def __init__(self, nb, sw=12, sh=6):
+        self.nb, self.sw, self.sh = nb, sw, sh
+        self.sc = self.r0 = self.j = self.base = 0
+
+    def seek(self, t):
+        while True:
+            w = min(self.sw, self.nb - self.sc)
+            r1 = min(self.r0 + self.sh, self.nb)
+            lo = max(self.r0, self.j)
+            cnt = r1 - lo
+            if cnt > 0:
+                if t < self.base + cnt:
+                    return lo + (t - self.base), self.j
+                self.base += cnt
+            self.j += 1
+            if self.j >= self.sc + w:
+                self.r0 += self.sh
+                self.j = self.sc
+                if self.r0 >= self.nb:
+                    self.sc += self.sw
+                    self.r0 = self.j = self.sc
+                    if self.sc >= self.nb:
+                        return self.nb - 1, 0

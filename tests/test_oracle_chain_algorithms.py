@@ -67,3 +67,18 @@ def test_syrk_tile_order_touches_fewer_channels_per_wave():
     nbm = 86
     naive = [(bi, bj) for bj in range((nbm + 1) // 2) for bi in range(2 * bj, nbm)]       # column by column
     assert footprint(C.syrk_tile_order(nbm, 12, 12)) <= 0.75 * footprint(naive)
+
+
+@pytest.mark.parametrize("nb,sw,sh", [(1, 12, 6), (3, 12, 6), (16, 12, 6), (43, 12, 6), (43, 8, 9), (144, 12, 6), (7, 3, 2)])
+def test_syrk2_tile_order_and_forward_walk(nb, sw, sh):
+    """The CTA-pair Hessian kernel's tile order visits every tile touching the lower triangle exactly once, and the forward
+    walker (one per kernel role, advanced with the cluster's stride) reproduces it for every start and stride."""
+    from oracle.chain_algorithms import syrk2_tile_order, Syrk2TileWalk
+    order = syrk2_tile_order(nb, sw, sh)
+    assert sorted(order) == sorted((bi, bj) for bj in range(nb) for bi in range(bj, nb))
+    n = len(order)
+    for stride in (1, 5, 74):
+        for start in range(min(stride, n)):
+            walk = Syrk2TileWalk(nb, sw, sh)
+            for t in range(start, n, stride):
+                assert walk.seek(t) == order[t]
