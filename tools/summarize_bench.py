@@ -34,10 +34,13 @@ def keep(src, dst):
 
 lines = ["# Round 2: bench lines (`bench.py` on the GPU box; full JSON beside this file)", ""]
 layer = {}
-for n, src in ((1, "r2_bench_final_n1.json"), (2, "r2_bench_n2.json"), (4, "r2_bench_n4.json"), (8, "r2_bench_n8.json")):
-    d = keep(src, f"r02_bench_n{n}.json")
+# N = 1, 2, 4, 8 back to back on ONE 8-GPU box (tools/gpu_call_8.sh); the N = 1 line with the CPU / GPU-torch baselines comes from a
+# separate 1-GPU box (tools/gpu_call13.sh)
+for n, src in ((1, "r2_scale_n1.json"), (2, "r2_scale_n2.json"), (4, "r2_scale_n4.json"), (8, "r2_scale_n8.json")):
+    d = keep(src, f"r02_bench_n{n}.json" if n > 1 else "r02_bench_n1_scaling_box.json")
     if d:
         layer[n] = d
+full1 = keep("r2_bench_final_n1.json", "r02_bench_n1.json")
 if layer:
     lines += ["## Llama-2-7B decoder layer, 4-bit g128 act-order static groups, 128 x 2048 tokens (BASELINE configs[2])", "",
               "| GPUs | ms/step | Mweights/s | e2e ms/step (host buffers) | e2e Mweights/s | Hessian | chain | column loop | prologue | staging+rest | Hessian TFLOP/s issued | frac of 2250 |",
@@ -50,8 +53,16 @@ if layer:
                      f"{ph.get('syrk', 0):.1f} | {ph.get('hinv_upper', 0):.1f} | {ph.get('colloop', 0):.1f} | {ph.get('prologue', 0):.1f} | {rest:.1f} | "
                      f"{d['roofline']['achieved']:.0f} | {d['roofline']['frac_of_nominal_2250']:.3f} |")
     lines.append("")
-    d1 = layer.get(1)
+    if layer.get(1):
+        b = layer[1]["value"]
+        lines.append("Scaling efficiency (value(N) / (N x value(1)), same box): " + ", ".join(
+            f"N={n}: {d['value'] / b / n:.2f}" for n, d in sorted(layer.items())) + ".")
+        lines.append("")
+    d1 = full1
     if d1:
+        lines.append(f"N = 1 on a separate 1-GPU box with both baselines in the same run (`profiles/r02_bench_n1.json`): {d1['ms_per_step']:.1f} ms/step, "
+                     f"{d1['value']:.0f} Mweights/s, e2e {d1['e2e']['ms_per_step']:.1f} ms/step = {d1['e2e']['value']:.0f} Mweights/s, Hessian "
+                     f"{d1['roofline']['achieved']:.0f} TFLOP/s issued.")
         cb, gb = d1.get("cpu_baseline"), d1.get("gpu_torch_baseline")
         if cb:
             lines.append(f"CPU baseline ({cb['kind']}, {cb['cores']} threads, bounded sample): {cb['value']:.2f} Mweights/s "
