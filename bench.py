@@ -652,6 +652,11 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if os.environ.get("GPTQ_B200_EXPANDABLE_SEGMENTS", "1") == "1":
+        # same allocator setting as the whole-model driver (bench_model.py): the K x K and R x K fp32 buffers
+        # of the solver (64 - 485 MB each) otherwise make the caching allocator call cudaMalloc / cudaFree inside steps
+        # whenever its block-splitting pattern shifts (seen as single steps with a 50 - 170 ms "prologue")
+        torch.cuda.memory._set_allocator_settings("expandable_segments:True")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -663,6 +668,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     STEP_MS = []
+    ALLOC = {}
 
     def timed(acts, weights, from_host, steps, warmup, profile):
         quiet = io.StringIO()
@@ -679,6 +685,7 @@ def run_ours(args):
             gc.disable()
             barrier()
             G.PROFILE = [] if profile else None
+            ms0 = torch.cuda.memory_stats(dev)
             n0 = _lib.launch_count()
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
@@ -695,6 +702,9 @@ def run_ours(args):
             wall = time.perf_counter() - t0
             gc.enable()
             gc.unfreeze()
+            ms1 = torch.cuda.memory_stats(dev)
+            ALLOC.clear()
+            ALLOC.update({k: ms1.get(k, 0) - ms0.get(k, 0) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")})
         ms = e0.elapsed_time(e1)
         STEP_MS.clear()
         STEP_MS.extend(round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 2) for i in range(steps))
@@ -719,6 +729,7 @@ def run_ours(args):
             time.sleep(0.05)
     ms, wall, launches, prof, _ = timed(acts, weights, False, args.steps, args.warmup, True)
     step_ms_each = list(STEP_MS)
+    alloc_timed = dict(ALLOC, expandable_segments=os.environ.get("GPTQ_B200_EXPANDABLE_SEGMENTS", "1") == "1")
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms / args.steps
     value = wl["weights"] / (ms_step / 1e3) / 1e6
@@ -807,7 +818,8 @@ def run_ours(args):
                     "hessian_tflops_issued": syrk_tflops, "hessian_tflops_dense_equivalent": dense_equiv,
                     "roofline": roofline, "rooflines_other": others, "phase_ms_per_step": phase_ms,
                     "phase_breakdown_instrumented_step": fine, "clocks": clocks, "e2e": e2e,
-                    "gpu_launches": launches, "impl": "ours", "ms_each_step_rank0": step_ms_each})
+                    "gpu_launches": launches, "impl": "ours", "ms_each_step_rank0": step_ms_each,
+                    "allocator_timed_region_rank0": alloc_timed})
         if parity is not None:
             out["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:

@@ -56,6 +56,7 @@ SIGNATURES = {
     "gptq_b200_sgemm": (_i, [_i, _i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _f, _vp, _i64, _vp]),
     "gptq_b200_gemm3x": (_i, [_i, _i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _f, _vp, _i64, _vp]),
     "gptq_b200_set_gemm_backend": (_i, [_i]),
+    "gptq_b200_set_chain_schedule": (_i, [_i, _i]),
 }
 
 _lib = None

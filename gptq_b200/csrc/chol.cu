@@ -15,6 +15,8 @@
 #include "sgemm.cuh"
 #include "ptx.cuh"
 #include <stdlib.h>
+#include <mutex>
+#include <vector>
 
 namespace gq {
 
@@ -519,17 +521,217 @@ static void hinv_rec(HinvCtx& c, int a, int b) {
     c.rc = gemm_fp32(0, 0, n1, n2, n2, -1.f, c.S, n2, V22, c.ldv, 0.f, V12, c.ldv, SG_B_UPPER, c.st);
 }
 
+// ------------------------------------------------------------------ right-looking driver with look-ahead
+// The recursion above keeps every flop in a large-k GEMM but runs strictly in sequence: while one SM factors a diagonal
+// block (48.5 us) or a 128..256-wide GEMM of the lowest levels runs, the other SMs idle -- 2/3 of the chain's time at
+// K = 4096 and 11008.  This driver keeps the recursion for PANELS of `pb` blocks and overlaps the rest on three
+// internal streams (forked from / joined into the caller's stream with events; the call stays asynchronous and ordered
+// on the caller's stream).  Panels p = [e0, e1) are processed from the last to the first; q = [f0, f1), f1 = e0, is the next:
+//
+//   critical stream   hinv_rec(p)                              V_pp = R_pp^-1 and R inside the panel
+//                     wait trail(p+1)
+//                     Tt_p[:, q]  = V_pp A[q, p]^T             look-ahead solve: only the columns of the next panel
+//                     record rec(p)
+//                     A[q, q]    -= Tt_p[:, q]^T Tt_p[:, q]    the one block the next hinv_rec needs
+//   trailing stream   wait rec(p)
+//                     Tt_p[:, 0:f0] = V_pp A[0:f0, p]^T        rest of the panel solve
+//                     A[0:f0, 0:f1] -= Tt_p[:, 0:f0]^T Tt_p[:, 0:f1]   (upper tiles)    rank-|p| trailing update
+//                     record trail(p)
+//   inverse stream    wait rec(p)
+//                     S = R[p, e1:] V[e1:, e1:];  V[p, e1:] = -V_pp S     row block p of U (needs only finished panels)
+//
+// Every (block, source panel) update is applied exactly once and in a fixed order (trail(p+1) before the look-ahead
+// update of p, enforced by the event), so the result does not depend on how the streams interleave.
+// Tt_p lives in A's lower mirror A[p, 0:e0] like in the recursion.
+struct ChainStreams {
+    cudaStream_t crit = nullptr, trail = nullptr, inv = nullptr;
+    cudaEvent_t fork = nullptr, join_c = nullptr, join_t = nullptr, join_i = nullptr;
+    std::vector<cudaEvent_t> rec, trl;
+};
+static std::mutex g_chain_mu;                       // one look-ahead chain is being ISSUED at a time (they share the event pool)
+static ChainStreams g_chain_streams[64];
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+static int g_chain_lookahead = env_int("GPTQ_B200_CHAIN_LOOKAHEAD", 1);     // 0: the plain recursion
+static int g_chain_panel = env_int("GPTQ_B200_CHAIN_PANEL", 0);             // blocks per panel; 0 = by size (panel_blocks)
+static int g_chain_min_blocks = env_int("GPTQ_B200_CHAIN_MIN_BLOCKS", 8);   // fewer blocks: the recursion as it is
+// TIMING EXPERIMENTS ONLY (results are wrong when set): bit 0 = issue nothing on the inverse stream, bit 1 = nothing on the
+// trailing stream -- what is left is the critical stream alone (tools/chain_lab.py).
+static int g_chain_skip = env_int("GPTQ_B200_CHAIN_SKIP", 0);
+// GPTQ_B200_CHAIN_TRACE=1: timing events around every phase of every panel; the call then SYNCHRONISES and prints one line
+// per panel to stderr (microseconds since the fork).  Diagnostics only.
+static int g_chain_trace = env_int("GPTQ_B200_CHAIN_TRACE", 0);
+struct ChainTrace {
+    bool on;
+    cudaEvent_t t0 = nullptr;
+    std::vector<std::vector<cudaEvent_t>> ev;          // [panel][slot]
+    enum { REC0, REC1, SOLVE0, UPD1, TR0, TR1, INV0, INV1, NSLOT };
+    void init(int np) {
+        if (!on) return;
+        cudaEventCreate(&t0);
+        ev.assign(np, std::vector<cudaEvent_t>(NSLOT, nullptr));
+    }
+    void mark(int panel, int slot, cudaStream_t st) {
+        if (!on) return;
+        cudaEventCreate(&ev[panel][slot]);
+        cudaEventRecord(ev[panel][slot], st);
+    }
+    void dump(cudaStream_t st) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        static const char* names[NSLOT] = {"rec0", "rec1", "solve0", "upd1", "trail0", "trail1", "inv0", "inv1"};
+        for (int i = (int)ev.size() - 1; i >= 0; --i) {
+            fprintf(stderr, "chain_trace panel %d", i);
+            for (int k = 0; k < NSLOT; ++k) {
+                float ms = -1.f;
+                if (ev[i][k]) { cudaEventElapsedTime(&ms, t0, ev[i][k]); cudaEventDestroy(ev[i][k]); }
+                fprintf(stderr, " %s=%.1f", names[k], ms < 0 ? -1.0 : ms * 1e3);
+            }
+            fprintf(stderr, "\n");
+        }
+        cudaEventDestroy(t0);
+    }
+};
+
+// Measured on B200 (tools/chain_sweep.py, profiles/r02_chain_lookahead.md): up to K = 4096 the chain is bound by the critical
+// stream, whose cost per block is lowest with one block per panel (diag + two 128^3 products); from K ~ 8192 on it is bound
+// by the throughput of the rank-|panel| trailing updates and the |panel|-row inverse products, which need k = M = 1024 to
+// run the tensor-core GEMM near its rate.
+static int panel_blocks(int nb) {
+    if (g_chain_panel > 0) return g_chain_panel;
+    return nb <= 36 ? 1 : nb <= 56 ? 2 : 8;
+}
+static bool use_lookahead(int nb) {
+    return g_chain_lookahead && nb >= g_chain_min_blocks && nb > 2 * panel_blocks(nb);
+}
+
+static size_t rec_scratch_floats(size_t nb) {
+    size_t s = (nb / 2) * CB * ((nb - nb / 2) * CB);
+    return s < (size_t)CB * CB ? (size_t)CB * CB : s;
+}
+
+static int chain_streams(ChainStreams** out, int npanels) {
+    const int dev = cur_device();
+    if (dev < 0 || dev >= 64) return set_err(-1, "hinv_upper: device ordinal %d out of range", dev);
+    ChainStreams& cs = g_chain_streams[dev];
+    if (!cs.crit) {
+        int least = 0, greatest = 0;
+        GQ_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));      // numerically lower = higher priority
+        const int mid = greatest < least ? greatest + 1 : least;
+        const bool inv_first = env_int("GPTQ_B200_CHAIN_INV_PRIO", 0) != 0;
+        GQ_CUDA(cudaStreamCreateWithPriority(&cs.crit, cudaStreamNonBlocking, greatest));
+        GQ_CUDA(cudaStreamCreateWithPriority(&cs.trail, cudaStreamNonBlocking, inv_first ? least : mid));
+        GQ_CUDA(cudaStreamCreateWithPriority(&cs.inv, cudaStreamNonBlocking, inv_first ? mid : least));
+        for (cudaEvent_t* e : {&cs.fork, &cs.join_c, &cs.join_t, &cs.join_i}) GQ_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    while ((int)cs.rec.size() < npanels) {
+        cudaEvent_t a, b;
+        GQ_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        GQ_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        cs.rec.push_back(a); cs.trl.push_back(b);
+    }
+    *out = &cs;
+    return 0;
+}
+
+#define GQ_RC(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+static int hinv_lookahead(float* A, int nb, int64_t lda, float* V, int64_t ldv, int32_t* info, float* ws, size_t smem,
+                          cudaStream_t st) {
+    const int pb = panel_blocks(nb);
+    const int np = (nb + pb - 1) / pb;
+    const int Kp = nb * CB;
+    std::lock_guard<std::mutex> lock(g_chain_mu);
+    ChainStreams* cs = nullptr;
+    GQ_RC(chain_streams(&cs, np));
+    float* S_inv = ws;                                       // [panel rows x columns right of the panel], inverse stream
+    float* S_rec = ws + (size_t)pb * CB * Kp;                // scratch of the in-panel recursion, critical stream
+    ChainTrace tr{g_chain_trace != 0};
+    tr.init(np);
+    if (tr.on) cudaEventRecord(tr.t0, st);
+    GQ_CUDA(cudaEventRecord(cs->fork, st));
+    GQ_CUDA(cudaStreamWaitEvent(cs->crit, cs->fork, 0));
+    HinvCtx c{A, lda, V, ldv, S_rec, info, cs->crit, smem, 0, true};
+    // panel i (i = np-1 .. 0) covers blocks [max(0, nb - (np - i) pb), nb - (np - 1 - i) pb): the short panel is the first one
+    for (int i = np - 1; i >= 0; --i) {
+        const int b1 = nb - (np - 1 - i) * pb, b0 = (b1 - pb > 0) ? b1 - pb : 0;
+        const int64_t e0 = (int64_t)b0 * CB, e1 = (int64_t)b1 * CB;
+        const int P = (int)(e1 - e0);
+        const bool last = (i == np - 1);
+        tr.mark(i, ChainTrace::REC0, cs->crit);
+        hinv_rec(c, b0, b1);
+        if (c.rc) return c.rc;
+        tr.mark(i, ChainTrace::REC1, cs->crit);
+        const float* Vpp = V + e0 * ldv + e0;
+        float* Tt = A + e0 * lda;                            // Tt_p, [P x e0]
+        if (i > 0) {
+            const int a0 = (b0 - pb > 0) ? b0 - pb : 0;
+            const int64_t f0 = (int64_t)a0 * CB;
+            const int Q = (int)(e0 - f0);
+            int nopdl = 0;
+            if (!last) { GQ_CUDA(cudaStreamWaitEvent(cs->crit, cs->trl[i + 1], 0)); nopdl = SG_NO_PDL; }
+            tr.mark(i, ChainTrace::SOLVE0, cs->crit);
+            GQ_RC(gemm_fp32(0, 1, P, Q, P, 1.f, Vpp, ldv, A + f0 * lda + e0, lda, 0.f, Tt + f0, lda, SG_A_UPPER | nopdl, cs->crit));
+            GQ_CUDA(cudaEventRecord(cs->rec[i], cs->crit));
+            GQ_RC(gemm_fp32(1, 0, Q, Q, P, -1.f, Tt + f0, lda, Tt + f0, lda, 1.f, A + f0 * lda + f0, lda, SG_UPPER_TILES, cs->crit));
+            tr.mark(i, ChainTrace::UPD1, cs->crit);
+            // trailing stream
+            GQ_CUDA(cudaStreamWaitEvent(cs->trail, cs->rec[i], 0));
+            tr.mark(i, ChainTrace::TR0, cs->trail);
+            if (f0 > 0 && !(g_chain_skip & 2)) {
+                GQ_RC(gemm_fp32(0, 1, P, (int)f0, P, 1.f, Vpp, ldv, A + e0, lda, 0.f, Tt, lda, SG_A_UPPER | SG_NO_PDL, cs->trail));
+                GQ_RC(gemm_fp32(1, 0, (int)f0, (int)e0, P, -1.f, Tt, lda, Tt, lda, 1.f, A, lda, SG_UPPER_TILES, cs->trail));
+            }
+            tr.mark(i, ChainTrace::TR1, cs->trail);
+            GQ_CUDA(cudaEventRecord(cs->trl[i], cs->trail));
+        } else {
+            GQ_CUDA(cudaEventRecord(cs->rec[i], cs->crit));
+        }
+        // inverse stream: row block i of U right of its diagonal block
+        if (!last && !(g_chain_skip & 1)) {
+            const int nl = (int)(Kp - e1);
+            GQ_CUDA(cudaStreamWaitEvent(cs->inv, cs->rec[i], 0));
+            tr.mark(i, ChainTrace::INV0, cs->inv);
+            GQ_RC(gemm_fp32(1, 0, P, nl, nl, 1.f, A + e1 * lda + e0, lda, V + e1 * ldv + e1, ldv, 0.f, S_inv, nl,
+                            SG_B_UPPER | SG_NO_PDL, cs->inv));
+            GQ_RC(gemm_fp32(0, 0, P, nl, P, -1.f, Vpp, ldv, S_inv, nl, 0.f, V + e0 * ldv + e1, ldv, SG_A_UPPER, cs->inv));
+            tr.mark(i, ChainTrace::INV1, cs->inv);
+        }
+    }
+    GQ_CUDA(cudaEventRecord(cs->join_c, cs->crit));
+    GQ_CUDA(cudaEventRecord(cs->join_t, cs->trail));
+    GQ_CUDA(cudaEventRecord(cs->join_i, cs->inv));
+    GQ_CUDA(cudaStreamWaitEvent(st, cs->join_c, 0));
+    GQ_CUDA(cudaStreamWaitEvent(st, cs->join_t, 0));
+    GQ_CUDA(cudaStreamWaitEvent(st, cs->join_i, 0));
+    tr.dump(st);
+    return 0;
+}
+
 }  // namespace gq
 
 using namespace gq;
 
 extern "C" size_t gptq_b200_hinv_upper_workspace_bytes(int Kp) {
     if (Kp <= 0) return 0;
-    size_t nb = (size_t)(Kp / CB);
-    size_t h1 = (nb / 2) * CB, h2 = (nb - nb / 2) * CB;
-    size_t s = h1 * h2;                                  // largest n1 x n2 scratch (top-level split)
-    if (s < (size_t)CB * CB) s = (size_t)CB * CB;
+    const size_t nb = (size_t)(Kp / CB);
+    size_t s = rec_scratch_floats(nb);                   // the recursion: largest n1 x n2 scratch (top-level split)
+    if (use_lookahead((int)nb)) {
+        const size_t pb = (size_t)panel_blocks((int)nb);
+        const size_t la = pb * CB * Kp + rec_scratch_floats(pb);
+        if (la > s) s = la;
+    }
     return s * sizeof(float);
+}
+
+extern "C" int gptq_b200_set_chain_schedule(int lookahead, int panel_blocks) {
+    GQ_ARG(panel_blocks <= 64, 2, "panel_blocks must be 0 (by size) .. 64 (negative: keep)");
+    if (lookahead >= 0) g_chain_lookahead = lookahead ? 1 : 0;
+    if (panel_blocks >= 0) g_chain_panel = panel_blocks;
+    return 0;
 }
 
 extern "C" int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, float* U, int64_t ldu, int32_t* info, void* ws,
@@ -544,9 +746,14 @@ extern "C" int gptq_b200_hinv_upper(float* A, int Kp, int64_t lda, float* U, int
     GQ_ONCE_PER_DEVICE(GQ_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)));
     GQ_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     GQ_CUDA(cudaMemset2DAsync(U, ldu * sizeof(float), 0, (size_t)Kp * sizeof(float), Kp, st));
-    HinvCtx c{A, lda, U, ldu, static_cast<float*>(ws), info, st, smem, 0, true};
-    hinv_rec(c, 0, Kp / CB);
-    if (c.rc) return c.rc;
+    if (use_lookahead(Kp / CB)) {
+        int rc = hinv_lookahead(A, Kp / CB, lda, U, ldu, info, static_cast<float*>(ws), smem, st);
+        if (rc) return rc;
+    } else {
+        HinvCtx c{A, lda, U, ldu, static_cast<float*>(ws), info, st, smem, 0, true};
+        hinv_rec(c, 0, Kp / CB);
+        if (c.rc) return c.rc;
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err((int)e, "hinv_upper: launch failed: %s", cudaGetErrorString(e));
     return 0;

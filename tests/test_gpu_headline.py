@@ -39,7 +39,19 @@ if torch.cuda.is_available():
 # same rows the oracle flips against ITSELF when its factor is computed in fp64 -- the control below); 2^-18 leaves a factor
 # of 8.  With the Hessian from the tcgen05 syrk (~2e-6 relative from the reference's fp32 sgemm) the perturbation of w/scale
 # grows accordingly; 2^-14 of a step is the tolerance there.  Act-order adds sort-key ties (see O.classify_mismatches).
+#
+# The resolution grows with K: at K = 11008 the reference does not reproduce ITSELF below ~6e-6 of a step -- the oracle with
+# its upper factor computed in fp64 instead of fp32 flips 11 of 512 rows of a down_proj-shaped layer, first-divergence margins
+# up to 6.1e-6 (tools/control_chain_sensitivity.py -> tests/golden/control_chain_sensitivity_k11008.json; none at K = 4096).
+# The two schedules of the CUDA chain (block recursion / look-ahead panels) land on different sides of such near-ties
+# (measured 4.3e-6 with the look-ahead schedule), so K > 4096 gets 2^-16 with the same H.
 TIE_TOL = {"same_H": 2.0 ** -18, "gpu_H": 2.0 ** -14}
+TIE_TOL_LARGE_K = {"same_H": 2.0 ** -16, "gpu_H": 2.0 ** -14}
+
+
+def _tie_tol(mode, K):
+    return (TIE_TOL_LARGE_K if K > 4096 else TIE_TOL)[mode]
+
 PERM_TOL = 1e-5          # relative agreement of two diag(H) values that may legitimately swap places in the act-order
 
 
@@ -97,10 +109,10 @@ def _check_case(cfg):
         ctl = O.fasterquant(W16, Href, O.QParams(bits=cfg["bits"]), blocksize=cfg.get("blocksize", 128),
                             groupsize=cfg.get("groupsize", -1), actorder=cfg.get("actorder", False),
                             static_groups=cfg.get("static_groups", False), chain_fp64=True, stable_perm=True)
-        _log(test="headline_control_oracle_fp64_chain_vs_oracle", case=cfg["name"], **O.classify_mismatches(ctl.codes, ref, TIE_TOL["same_H"]))
+        _log(test="headline_control_oracle_fp64_chain_vs_oracle", case=cfg["name"], **O.classify_mismatches(ctl.codes, ref, _tie_tol("same_H", K)))
     for mode in cfg.get("modes", ("same_H", "gpu_H")):
         lin, g = _gpu_run(W16, batches, cfg, Href if mode == "same_H" else None)
-        cls = O.classify_mismatches(g.codes, ref, TIE_TOL[mode], perm=g.perm, diag=torch.diag(Href), perm_tol=PERM_TOL)
+        cls = O.classify_mismatches(g.codes, ref, _tie_tol(mode, K), perm=g.perm, diag=torch.diag(Href), perm_tol=PERM_TOL)
         rel_err = abs(g.error - ref.error) / abs(ref.error)
         rec_gpu = O.recon_error(W16.float(), lin.weight.data.cpu().float(), Href)
         _log(test="headline", case=cfg["name"], H=mode, err_gpu=g.error, err_ref=ref.error, recon_gpu=rec_gpu, recon_ref=rec_ref,

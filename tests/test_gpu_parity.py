@@ -183,6 +183,50 @@ def test_hinv_upper_vs_fp64(K):
     assert e_gpu < max(5 * e_ref, 1e-5)
 
 
+@pytest.mark.parametrize("K,panel", [(1024, 2), (1408, 0), (1408, 1), (2304, 4), (2176, 3), (4096, 0), (5120, 0), (7296, 0)])
+def test_hinv_upper_lookahead_schedule(K, panel):
+    """Right-looking panels with look-ahead on three internal streams (csrc/chol.cu hinv_lookahead; CPU restatement and
+    race check of the schedule: oracle/chain_algorithms.py LookaheadSchedule) against the plain recursion and fp64:
+    as close to fp64 as the recursion, and bitwise reproducible from run to run (every update is applied once, in an
+    order fixed by the events, whatever the streams' interleaving)."""
+    lib = _lib.load()
+    H = _spd(K, K + panel)
+    Hd = H.double().clone()
+    Hd += torch.eye(K, dtype=torch.float64) * (0.01 * torch.mean(torch.diag(H)).double())
+    U64 = torch.linalg.cholesky(torch.cholesky_inverse(torch.linalg.cholesky(Hd)), upper=True)
+    try:
+        _lib.check(lib.gptq_b200_set_chain_schedule(0, -1), "set")
+        U_rec, info_rec, _ = _hinv_upper_gpu(H)
+        _lib.check(lib.gptq_b200_set_chain_schedule(1, panel), "set")
+        runs = [_hinv_upper_gpu(H) for _ in range(3)]
+    finally:
+        _lib.check(lib.gptq_b200_set_chain_schedule(1, 0), "set")
+    assert info_rec == 0 and all(r[1] == 0 for r in runs)
+    U_la = runs[0][0]
+    for r in runs[1:]:
+        assert torch.equal(r[0], U_la)
+    assert torch.all(torch.tril(U_la, -1) == 0)
+    e_rec, e_la = O.rel_fro(U_rec, U64), O.rel_fro(U_la, U64)
+    _log(test="hinv_upper_lookahead", K=K, panel=panel, rel_rec_vs_fp64=e_rec, rel_lookahead_vs_fp64=e_la,
+         rel_lookahead_vs_rec=O.rel_fro(U_la, U_rec))
+    assert e_la < max(3 * e_rec, 1e-6)
+
+
+def test_hinv_upper_lookahead_not_pd_and_other_stream():
+    """info is reported from the look-ahead schedule as well, and the call is ordered on a non-default caller stream."""
+    lib = _lib.load()
+    H = _spd(1280, 9)
+    Hbad = H.clone()
+    Hbad[700, 700] = -50.0
+    _, info, _ = _hinv_upper_gpu(Hbad)
+    assert info != 0
+    U0, info0, _ = _hinv_upper_gpu(H)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        U1, info1, _ = _hinv_upper_gpu(H)
+    assert info0 == 0 and info1 == 0 and torch.equal(U0, U1)
+
+
 def test_hinv_upper_not_pd():
     H = _spd(256, 5)
     H[100, 100] = -50.0

@@ -38,6 +38,32 @@ def test_recursion_equals_reference_route(nb, block):
     assert np.linalg.norm(V - U) <= 1e-9 * np.linalg.norm(U)
 
 
+@pytest.mark.parametrize("nb,pb", [(9, 2), (8, 2), (7, 3), (12, 4), (5, 1), (11, 2)])
+def test_lookahead_schedule_has_no_races_and_equals_reference_route(nb, pb):
+    """The three-stream schedule of hinv_lookahead (csrc/chol.cu): every pair of tasks that touch a common block with at
+    least one write is ordered by stream order or an event, and every order the events allow gives the same U."""
+    block = 8
+    sched = C.LookaheadSchedule(nb, pb, block)
+    assert sched.races() == []
+    H = _spd(nb * block, 100 + nb)
+    U = _reference_upper(H)
+    V = sched.run(H)
+    assert np.allclose(np.tril(V, -1), 0)
+    assert np.linalg.norm(V - U) <= 1e-9 * np.linalg.norm(U)
+    g = np.random.default_rng(nb * 31 + pb)
+    for _ in range(5):
+        assert np.array_equal(sched.run(H, sched.random_order(g)), V)
+
+
+def test_lookahead_schedule_detects_a_missing_wait():
+    """Control: without the wait for the previous trailing update the look-ahead solve races with it."""
+    sched = C.LookaheadSchedule(9, 2, 8)
+    for t in sched.tasks:
+        if t["name"].startswith("solveA"):
+            t["waits"] = ()
+    assert sched.races() != []
+
+
 def test_fused_block_reports_non_pd():
     H = _spd(16, 3)
     H[5, 5] = -1.0
