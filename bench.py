@@ -123,13 +123,34 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock and clock-event reasons of GPU `index`, sampled DURING the timed region.
+    GPTQ_B200_CLOCK_SAMPLER = nvml (default: NVML queries from a thread of this process every 100 ms), smi (an `nvidia-smi
+    -lms 200` child process, the round-1 sampler) or off."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.kind = os.environ.get("GPTQ_B200_CLOCK_SAMPLER", "nvml")
+        self.thread, self._stop, self.error = None, threading.Event(), None
 
     def start(self):
+        if self.kind == "off":
+            return
+        if self.kind == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.nv = pynvml
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+                self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+                self.thread = threading.Thread(target=self._poll, daemon=True)
+                self.thread.start()
+                return
+            except Exception as ex:              # fall back to the child process
+                self.error = repr(ex)
+                self.kind = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
@@ -138,25 +159,53 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        bits = [nv.nvmlClocksEventReasonHwSlowdown, nv.nvmlClocksEventReasonHwThermalSlowdown,
+                nv.nvmlClocksEventReasonSwThermalSlowdown, nv.nvmlClocksEventReasonSwPowerCap]
+        while not self._stop.is_set():
+            try:
+                t0 = time.perf_counter()
+                sm = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                t1 = time.perf_counter()
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                t2 = time.perf_counter()
+                pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                t3 = time.perf_counter()
+                self.call_ms = [max(a, b) for a, b in zip(getattr(self, "call_ms", [0, 0, 0]), [(t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3])]
+                self.rows.append([str(sm), str(self.mx), str(pw)] + ["Active" if (r & b) else "Not Active" for b in bits])
+            except Exception as ex:
+                self.error = repr(ex)
+            self._stop.wait(0.1)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.kind == "off":
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["sampler off (GPTQ_B200_CLOCK_SAMPLER=off)"]}
+        if self.kind == "nvml":
+            self._stop.set()
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+        elif self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        reasons = [n for i, n in enumerate(self.NAMES) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         load = sorted(sm)[len(sm) // 2:] if sm else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w_max": max(pw) if pw else None,
+                "source": "NVML, in-process thread, 100 ms" if self.kind == "nvml" else "nvidia-smi -lms 200",
+                "nvml_call_ms_max[clock,reasons,power]": [round(x, 2) for x in getattr(self, "call_ms", [])]}
 
 
 def metric_name(cfg):
@@ -669,15 +718,25 @@ def run_ours(args):
 
     STEP_MS = []
     ALLOC = {}
+    STEP_ALLOCS = []
 
     def timed(acts, weights, from_host, steps, warmup, profile):
         quiet = io.StringIO()
         d2h = 0
         with contextlib.redirect_stdout(quiet):
             G.PROFILE = [] if profile else None        # the warm-up runs exactly what the timed steps run (event pools included)
-            for _ in range(warmup):
-                quantize_layer(wl, dev, acts, weights, world, from_host)
+            # (the warm-up holds the previous step's results while the next step runs, exactly like the timed loop below: when
+            # it did not, the first timed steps had a higher memory peak than any warm-up step and the allocator grew its pool
+            # inside the timed region -- seven cuMemCreate / cuMemMap calls, each a driver round trip that occasionally
+            # collided with the clock sampler's NVML queries and showed up as one step of 200 - 900 ms, always the second)
+            _ = None
+            for _w in range(warmup):
+                _ = quantize_layer(wl, dev, acts, weights, world, from_host)
             carry = None
+            # slack in the allocator's pool: whatever the timed steps need beyond the warm-up's peak (block-splitting patterns
+            # shift from step to step) is served from memory that is already mapped
+            slack = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
+            del slack
             # Python's cyclic garbage collector is kept out of the timed region: with torch / transformers imported a
             # generation-2 pass walks millions of objects and showed up as single steps of 190 - 400 ms (stated in `config`)
             gc.collect()
@@ -697,6 +756,7 @@ def run_ours(args):
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 marks.append(ev)
+                STEP_ALLOCS.append(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))
             e1.record()
             barrier()
             wall = time.perf_counter() - t0
@@ -705,6 +765,9 @@ def run_ours(args):
             ms1 = torch.cuda.memory_stats(dev)
             ALLOC.clear()
             ALLOC.update({k: ms1.get(k, 0) - ms0.get(k, 0) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")})
+            ALLOC["steps_with_device_alloc"] = [i for i, v in enumerate(STEP_ALLOCS)
+                                                if v != (STEP_ALLOCS[i - 1] if i else ms0.get("num_device_alloc", 0))]
+            STEP_ALLOCS.clear()
         ms = e0.elapsed_time(e1)
         STEP_MS.clear()
         STEP_MS.extend(round((e0 if i == 0 else marks[i - 1]).elapsed_time(marks[i]), 2) for i in range(steps))

@@ -538,7 +538,8 @@ static void hinv_rec(HinvCtx& c, int a, int b) {
 //                     A[0:f0, 0:f1] -= Tt_p[:, 0:f0]^T Tt_p[:, 0:f1]   (upper tiles)    rank-|p| trailing update
 //                     record trail(p)
 //   inverse stream    wait rec(p)
-//                     S = R[p, e1:] V[e1:, e1:];  V[p, e1:] = -V_pp S     row block p of U (needs only finished panels)
+//                     V[p, e1:] = -V_pp S_p                    row block p of U, with the S_p issued one panel earlier
+//                     S_q = R[q, e0:] V[e0:, e0:]              for the NEXT panel: needs only finished panels
 //
 // Every (block, source panel) update is applied exactly once and in a fixed order (trail(p+1) before the look-ahead
 // update of p, enforced by the event), so the result does not depend on how the streams interleave.
@@ -690,14 +691,26 @@ static int hinv_lookahead(float* A, int nb, int64_t lda, float* V, int64_t ldv, 
         } else {
             GQ_CUDA(cudaEventRecord(cs->rec[i], cs->crit));
         }
-        // inverse stream: row block i of U right of its diagonal block
-        if (!last && !(g_chain_skip & 1)) {
-            const int nl = (int)(Kp - e1);
+        // inverse stream: row block i of U right of its diagonal block,  V[p, e1:] = -V_pp S_p  with  S_p = R[p, e1:] V[e1:, e1:].
+        // S_p needs nothing of panel p itself (its rows of R were written by the solves of the later panels, V[e1:, e1:] is
+        // complete once the row block of panel i+1 is), so it was issued one iteration earlier and ran while panel p was
+        // being factored; what is left after the last panel is one |p| x |p| product per row block.
+        if (!(g_chain_skip & 1)) {
             GQ_CUDA(cudaStreamWaitEvent(cs->inv, cs->rec[i], 0));
             tr.mark(i, ChainTrace::INV0, cs->inv);
-            GQ_RC(gemm_fp32(1, 0, P, nl, nl, 1.f, A + e1 * lda + e0, lda, V + e1 * ldv + e1, ldv, 0.f, S_inv, nl,
-                            SG_B_UPPER | SG_NO_PDL, cs->inv));
-            GQ_RC(gemm_fp32(0, 0, P, nl, P, -1.f, Vpp, ldv, S_inv, nl, 0.f, V + e0 * ldv + e1, ldv, SG_A_UPPER, cs->inv));
+            int nopdl = SG_NO_PDL;
+            if (!last) {
+                const int nl = (int)(Kp - e1);
+                GQ_RC(gemm_fp32(0, 0, P, nl, P, -1.f, Vpp, ldv, S_inv, nl, 0.f, V + e0 * ldv + e1, ldv, SG_A_UPPER | nopdl, cs->inv));
+                nopdl = 0;
+            }
+            if (i > 0) {                                     // S of the NEXT panel q = [f0, e0): columns right of it = [e0, Kp)
+                const int a0 = (b0 - pb > 0) ? b0 - pb : 0;
+                const int64_t f0 = (int64_t)a0 * CB;
+                const int Q = (int)(e0 - f0), nl = (int)(Kp - e0);
+                GQ_RC(gemm_fp32(1, 0, Q, nl, nl, 1.f, A + e0 * lda + f0, lda, V + e0 * ldv + e0, ldv, 0.f, S_inv, nl,
+                                SG_B_UPPER | nopdl, cs->inv));
+            }
             tr.mark(i, ChainTrace::INV1, cs->inv);
         }
     }

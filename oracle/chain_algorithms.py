@@ -62,7 +62,7 @@ class LookaheadSchedule:
     Panels of `pb` blocks, last to first; p = [e0, e1), next q = [f0, f1 = e0):
         crit : rec(p)  [wait trail(p+1)]  Tt_p[:, q] = V_pp A[q, p]^T   record rec(p)   A[q, q] -= Tt_p[:, q]^T Tt_p[:, q]
         trail: wait rec(p)   Tt_p[:, :f0] = V_pp A[:f0, p]^T   A[:f0, :f1] -= Tt_p[:, :f0]^T Tt_p[:, :f1]   record trail(p)
-        inv  : wait rec(p)   S = R[p, e1:] V[e1:, e1:]   V[p, e1:] = -V_pp S
+        inv  : wait rec(p)   V[p, e1:] = -V_pp S_p   S_q = R[q, e0:] V[e0:, e0:]   (S of the NEXT panel: it needs nothing of q)
     """
 
     def __init__(self, nb, pb=2, block=128, leaf=fused_block):
@@ -126,16 +126,22 @@ class LookaheadSchedule:
                     add("trail", f"trailB{i}", set(), set(), lambda A, V, S: None, waits=(f"rec{i}",), record=f"trail{i}")
             else:
                 add("crit", f"mark{i}", set(), set(), lambda A, V, S: None, record=f"rec{i}")
+            # inverse stream: V[p, e1:] = -V_pp S_p with the S_p that was issued one panel earlier, then S of the next panel
             if not last:
                 L = slice(b1 * B, nb * B)
 
-                def inv_s(A, V, S, P=P, L=L):
-                    S["inv"] = A[L, P].T @ V[L, L]
-                add("inv", f"invS{i}", rect("A", b1, nb, b0, b1) | rect("V", b1, nb, b1, nb), {("Sinv", 0, 0)}, inv_s, waits=(f"rec{i}",))
-
                 def inv_v(A, V, S, P=P, L=L):
                     V[P, L] = -V[P, P] @ S["inv"]
-                add("inv", f"invV{i}", rect("V", b0, b1, b0, b1) | {("Sinv", 0, 0)}, rect("V", b0, b1, b1, nb), inv_v)
+                add("inv", f"invV{i}", rect("V", b0, b1, b0, b1) | {("Sinv", 0, 0)}, rect("V", b0, b1, b1, nb), inv_v, waits=(f"rec{i}",))
+            if i > 0:
+                a0 = max(b0 - pb, 0)
+                Q = slice(a0 * B, b0 * B)
+                L2 = slice(b0 * B, nb * B)
+
+                def inv_s(A, V, S, Q=Q, L2=L2):
+                    S["inv"] = A[L2, Q].T @ V[L2, L2]
+                add("inv", f"invS{i - 1}", rect("A", b0, nb, a0, b0) | rect("V", b0, nb, b0, nb), {("Sinv", 0, 0)}, inv_s,
+                    waits=(f"rec{i}",) if last else ())
 
     def happens_before(self):
         """reach[i][j]: task i is ordered before task j by stream order and the events."""
