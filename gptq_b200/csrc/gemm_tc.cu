@@ -30,6 +30,7 @@ extern int g_gemm_splitk_minkb;
 extern int g_gemm_trunc;
 extern int g_gemm_bk;
 extern int g_small_gemm_max;
+extern int g_gemm_cprefetch;
 
 constexpr int GT_BM = 128, GT_BN = 256;
 constexpr int GT_RING_BYTES = 192 * 1024;             // operand ring: 2 stages of BK = 32 or 4 stages of BK = 16
@@ -42,6 +43,7 @@ constexpr int GT_TP = GT_BM + 4;                      // pitch of the transposed
 struct GemmTcParams {
     int M, N, Kd; float alpha, beta; float* C; int64_t ldc; int mode; int a_mn, b_mn; uint32_t idesc;
     int trunc;                                        // 1: the MMA reads the raw fp32 tile as `hi` (see the converter)
+    int cprefetch;                                    // 1: beta != 0 -> the C tile is pulled into L2 while the main loop runs
     int splits;                                       // cluster size along z: the k-range of a tile is split over the cluster
 };
 
@@ -197,6 +199,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int q = 0; q < 128; ++q) acc[q] = 0.f;
         int stage = 0; uint32_t phase = 0;
         int dbuf = 0; uint32_t dphase[2] = {0, 0};
+        if (p.cprefetch && p.beta != 0.f && S == 1) {
+            // the epilogue reads this thread's 512 bytes of C (4 dependent round trips to HBM otherwise): ask for the lines now
+            const int prow = m0 + quad * 32 + lane;
+            if (prow < p.M) {
+                const float* src = p.C + (int64_t)prow * p.ldc + n0 + half * 128;
+                const int ok = min(128, p.N - (n0 + half * 128));
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (q * 32 < ok) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + q * 32));
+            }
+        }
         auto drain = [&]() {
             ptx::mbar_wait(&tfull_bar[dbuf], dphase[dbuf]);
             ptx::tc_fence_after();
@@ -415,6 +428,7 @@ int gemm_tc_launch(int transa, int transb, int M, int N, int Kd, float alpha, co
         while (S * 2 <= 8 && tiles * S * 2 <= num_sms() && nkb / (S * 2) >= g_gemm_splitk_minkb) S *= 2;
     p.splits = S;
     p.trunc = g_gemm_trunc;
+    p.cprefetch = g_gemm_cprefetch;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(gx, gy, S);
     cfg.blockDim = dim3(GT_THREADS, 1, 1);
@@ -459,6 +473,7 @@ int g_gemm_bk = int_from_env("GPTQ_B200_GEMM_BK", 32);                // k-exten
 int g_gemm_trunc = int_from_env("GPTQ_B200_GEMM_TRUNC", 1);            // see the converter in gemm_tc_kernel
 int g_gemm_splitk_minkb = int_from_env("GPTQ_B200_SPLITK_MINKB", 4);   // fewest k-blocks (of 32) a split may get
 int g_pdl = flag_from_env("GPTQ_B200_PDL", 1);
+int g_gemm_cprefetch = flag_from_env("GPTQ_B200_GEMM_CPREFETCH", 1);
 
 int gemm_fp32(int transa, int transb, int M, int N, int Kd, float alpha, const float* A, int64_t lda, const float* B,
               int64_t ldb, float beta, float* C, int64_t ldc, int mode, cudaStream_t st) {
