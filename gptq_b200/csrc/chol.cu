@@ -599,14 +599,17 @@ struct ChainTrace {
 
 // Measured on B200 (tools/chain_sweep.py, profiles/r02_chain_lookahead.md): up to K = 4096 the chain is bound by the critical
 // stream, whose cost per block is lowest with one block per panel (diag + two 128^3 products); from K ~ 8192 on it is bound
-// by the throughput of the rank-|panel| trailing updates and the |panel|-row inverse products, which need k = M = 1024 to
-// run the tensor-core GEMM near its rate.
+// by the throughput of the rank-|panel| trailing updates and the |panel|-row inverse products, which need k = M >= 1024 to
+// run the tensor-core GEMM near its rate (K = 16384: 4096-wide panels); beyond ~24k columns the diagonal blocks are a few
+// per cent of the chain and the recursion's large square products win (K = 36864: 237 ms against 238-267).
+static int g_chain_max_blocks = env_int("GPTQ_B200_CHAIN_MAX_BLOCKS", 192);
 static int panel_blocks(int nb) {
     if (g_chain_panel > 0) return g_chain_panel;
-    return nb <= 36 ? 1 : nb <= 56 ? 2 : 8;
+    return nb <= 36 ? 1 : nb <= 56 ? 2 : nb <= 96 ? 8 : 32;
 }
 static bool use_lookahead(int nb) {
-    return g_chain_lookahead && nb >= g_chain_min_blocks && nb > 2 * panel_blocks(nb);
+    if (!g_chain_lookahead || nb < g_chain_min_blocks || nb <= 2 * panel_blocks(nb)) return false;
+    return g_chain_panel > 0 || nb <= g_chain_max_blocks;       // an explicit panel width (tests, sweeps) overrides the size limit
 }
 
 static size_t rec_scratch_floats(size_t nb) {
