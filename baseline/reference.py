@@ -37,8 +37,12 @@ def load():
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k in _NAMES or k.startswith("bcq_quant.")}
     sys.path.insert(0, REF_DIR)
     try:
-        import gptq as ref_gptq      # noqa: the reference's gptq.py
-        import quant as ref_quant    # noqa
+        # the reference prints "CUDA extension not installed." at import (quant.py, its optional quant_cuda module): keep the
+        # bench's stdout to its one JSON line
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):
+            import gptq as ref_gptq      # noqa: the reference's gptq.py
+            import quant as ref_quant    # noqa
     finally:
         sys.path.remove(REF_DIR)
         for k in list(sys.modules):
