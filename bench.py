@@ -122,6 +122,50 @@ def peaks():
     return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
+def _cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def numa_bind(local):
+    """Multi-GPU runs: pin this rank's main thread to the CPUs of the NUMA node its GPU hangs off BEFORE the pinned host
+    buffers are allocated, so that their pages are local to that node (first touch) and the rank's host-to-device stream does
+    not cross the socket interconnect.  What a multi-GPU calibration driver does with its pinned staging memory; a no-op when
+    the platform exposes no NUMA information (numa_node = -1), when the node has no CPU this process may use, or with
+    GPTQ_B200_NUMA_BIND=0.  Returns a description for the bench line."""
+    info = {"applied": False}
+    if os.environ.get("GPTQ_B200_NUMA_BIND", "1") != "1":
+        info["note"] = "disabled (GPTQ_B200_NUMA_BIND=0)"
+        return info
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        info["gpu_pci"] = bdf
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        use = sorted(set(cpus) & allowed)
+        info["node_cpus_allowed"] = len(use)
+        info["cpus_allowed_before"] = len(allowed)
+        if not use:
+            return info
+        os.sched_setaffinity(0, use)
+        info["applied"] = True
+    except Exception as ex:
+        info["error"] = repr(ex)
+    return info
+
+
 class ClockSampler:
     """SM clock and clock-event reasons of GPU `index`, sampled DURING the timed region.
     GPTQ_B200_CLOCK_SAMPLER = nvml (default: NVML queries from a thread of this process every 100 ms), smi (an `nvidia-smi
@@ -706,6 +750,7 @@ def run_ours(args):
         # of the solver (64 - 485 MB each) otherwise make the caching allocator call cudaMalloc / cudaFree inside steps
         # whenever its block-splitting pattern shifts (seen as single steps with a 50 - 170 ms "prologue")
         torch.cuda.memory._set_allocator_settings("expandable_segments:True")
+    numa = numa_bind(local) if world > 1 else {"applied": False, "note": "single GPU: not applied (the CPU baseline of this run uses every host thread)"}
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
@@ -736,7 +781,8 @@ def run_ours(args):
             # slack in the allocator's pool: whatever the timed steps need beyond the warm-up's peak (block-splitting patterns
             # shift from step to step) is served from memory that is already mapped
             slack = torch.empty(2 << 30, dtype=torch.uint8, device=dev)
-            del slack
+            small = [torch.empty(512 << 10, dtype=torch.uint8, device=dev) for _s in range(256)]   # the pool of blocks < 1 MB
+            del slack, small
             # Python's cyclic garbage collector is kept out of the timed region: with torch / transformers imported a
             # generation-2 pass walks millions of objects and showed up as single steps of 190 - 400 ms (stated in `config`)
             gc.collect()
@@ -882,7 +928,7 @@ def run_ours(args):
                     "roofline": roofline, "rooflines_other": others, "phase_ms_per_step": phase_ms,
                     "phase_breakdown_instrumented_step": fine, "clocks": clocks, "e2e": e2e,
                     "gpu_launches": launches, "impl": "ours", "ms_each_step_rank0": step_ms_each,
-                    "allocator_timed_region_rank0": alloc_timed})
+                    "allocator_timed_region_rank0": alloc_timed, "numa_rank0": numa})
         if parity is not None:
             out["parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
