@@ -58,6 +58,14 @@ if layer:
         lines.append("Scaling efficiency (value(N) / (N x value(1)), same box): " + ", ".join(
             f"N={n}: {d['value'] / b / n:.2f}" for n, d in sorted(layer.items())) + ".")
         lines.append("")
+    sb = os.path.join(PROF, "r02_bench_n8_second_box.json")
+    if os.path.exists(sb):
+        d8 = json.load(open(sb))
+        lines += [f"A second N = 8 run of the final build on another 8-GPU box (`profiles/r02_bench_n8_second_box.json`, `--steps {d8['steps']} "
+                  f"--warmup {d8['warmup']}`):", f"{d8['ms_per_step']:.1f} ms/step ({d8['value']:.0f} Mweights/s; steps "
+                  f"{min(d8['ms_each_step_rank0']):.1f}-{max(d8['ms_each_step_rank0']):.1f} ms), e2e {d8['e2e']['ms_per_step']:.1f} ms/step "
+                  f"({d8['e2e']['value']:.0f} Mweights/s).  Both 8-GPU boxes are single-NUMA-node VMs (`numa_node = -1`), so the NUMA-local",
+                  "placement of the pinned staging buffers (`numa_bind` in bench.py) is a no-op there.", ""]
     d1 = full1
     if d1:
         lines.append(f"N = 1 on a separate 1-GPU box with both baselines in the same run (`profiles/r02_bench_n1.json`): {d1['ms_per_step']:.1f} ms/step, "
