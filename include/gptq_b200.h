@@ -106,7 +106,13 @@ int gptq_b200_hessian_gather(const float* H, int K, int64_t ldh, const int32_t* 
  *     A (damped, [Kp,Kp], Kp % 128 == 0, upper triangle read) is DESTROYED; U ([Kp,Kp], a separate
  *     matrix) receives the upper factor of A^-1 (A^-1 = U^T U) with a zero strict lower triangle.
  *     Computed as U = R^-1 with A = R R^T (R upper): blocked backward Cholesky fused with a
- *     blocked triangular inverse in one recursion of fp32 GEMMs (chol.cu).
+ *     blocked triangular inverse (chol.cu).  From 8 blocks of 128 up to K = 24576 the work is
+ *     issued as right-looking panels with look-ahead on three library-internal streams that are
+ *     forked from `stream` and joined back into it with events before the call returns: for the
+ *     caller the call is asynchronous and ordered on `stream` like every other entry point (A,
+ *     U, info and ws must stay valid until work queued on `stream` after the call has run, as
+ *     usual); see gptq_b200_set_chain_schedule.  The result does not depend on how the internal
+ *     streams interleave (bitwise reproducible).
  *     *info (device int32): 0 ok, i+1 if the pivot at index i was not positive
  *     (torch.linalg.LinAlgError in the reference).
  * ------------------------------------------------------------------------------------------ */
