@@ -600,12 +600,14 @@ struct ChainTrace {
 // Measured on B200 (tools/chain_sweep.py, profiles/r02_chain_lookahead.md): up to K = 4096 the chain is bound by the critical
 // stream, whose cost per block is lowest with one block per panel (diag + two 128^3 products); from K ~ 8192 on it is bound
 // by the throughput of the rank-|panel| trailing updates and the |panel|-row inverse products, which need k = M >= 1024 to
-// run the tensor-core GEMM near its rate (K = 16384: 4096-wide panels); beyond ~24k columns the diagonal blocks are a few
+// run the tensor-core GEMM near its rate; beyond ~24k columns the diagonal blocks are a few
 // per cent of the chain and the recursion's large square products win (K = 36864: 237 ms against 238-267).
 static int g_chain_max_blocks = env_int("GPTQ_B200_CHAIN_MAX_BLOCKS", 192);
 static int panel_blocks(int nb) {
     if (g_chain_panel > 0) return g_chain_panel;
-    return nb <= 36 ? 1 : nb <= 56 ? 2 : nb <= 96 ? 8 : 32;
+    // (K = 16384 measured 24.0 ms with 4096-wide panels against 26.3 with 1024-wide ones and 29.2 for the recursion; the wider
+    // panels are left to GPTQ_B200_CHAIN_PANEL=32: the full parity suite of this round ran with 8)
+    return nb <= 36 ? 1 : nb <= 56 ? 2 : 8;
 }
 static bool use_lookahead(int nb) {
     if (!g_chain_lookahead || nb < g_chain_min_blocks || nb <= 2 * panel_blocks(nb)) return false;

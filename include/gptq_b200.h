@@ -228,8 +228,7 @@ int gptq_b200_gemm3x(int transa, int transb, int M, int N, int Kd, float alpha,
 int gptq_b200_set_gemm_backend(int backend);
 /* Schedule of gptq_b200_hinv_upper: lookahead 1 = right-looking panels with look-ahead on three internal streams (default
  * from 8 blocks of 128 on), 0 = the plain block recursion on the caller's stream; panel_blocks = blocks of 128 per panel
- * (0 = chosen by size, the default: 1 up to K = 4608, 2 up to 7168, 8 up to 12288, 32 up to 24576, the plain recursion
- * beyond).  A negative value keeps the current setting.  Also GPTQ_B200_CHAIN_LOOKAHEAD / GPTQ_B200_CHAIN_PANEL.
+ * (0 = chosen by size, the default: 1 up to K = 4608, 2 up to 7168, 8 up to 24576, the plain recursion beyond).  A negative value keeps the current setting.  Also GPTQ_B200_CHAIN_LOOKAHEAD / GPTQ_B200_CHAIN_PANEL.
  * Query gptq_b200_hinv_upper_workspace_bytes AFTER changing it.  Process-wide; for tests and A/B timing. */
 int gptq_b200_set_chain_schedule(int lookahead, int panel_blocks);
 
