@@ -23,3 +23,28 @@ def test_reference_arm_prints_one_json_line():
     e = d["e2e"]
     assert e["value"] == d["value"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """N > 1: the driver launches the reference arm like ours; rank 0 alone runs and prints, the others exit 0."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
+def test_bench_host_helpers():
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench._cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert bench._cpulist("") == []
+    info = bench.numa_bind(0)                      # no GPU here: reports why nothing was applied, never raises
+    assert info["applied"] is False
+    s = bench.ClockSampler(0)
+    s.kind = "off"
+    s.start()
+    assert s.stop()["sm_mhz"] is None
